@@ -1,0 +1,10 @@
+"""B200-native (sm_100a) hot path for imagined-speech EEG training.
+
+Host-side mirror of the reference's data-transform / model-module interface
+over the C ABI of libeegx.so (include/eegx.h).  No CPU fallback.
+"""
+from ._lib import EegxError, LIB_PATH  # noqa: F401
+from .preprocess import (DSP_CONFIG, DSP_CONFIG_LONG, REGION_ORDER, RegionNormalizer,  # noqa: F401
+                         SpectrogramFrontEnd, design_bandpass_fir, normalize_dense)
+
+__version__ = "0.1.0"

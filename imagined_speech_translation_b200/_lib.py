@@ -1,0 +1,79 @@
+"""ctypes binding of libeegx.so (the C ABI declared in include/eegx.h).
+
+There is no fallback: if the shared library is missing or the device is not a
+B200 (sm_100), every compute call raises.  Build with
+``python -m imagined_speech_translation_b200.build``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libeegx.so")
+
+_lib = None
+
+c_f32p = C.POINTER(C.c_float)
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_int_p = C.POINTER(C.c_int)
+
+# name -> (restype, argtypes); must list every symbol include/eegx.h declares
+# (tests/test_abi.py checks header <-> table <-> .so).
+SIGNATURES = {
+    "eegx_version": (C.c_int, []),
+    "eegx_last_error": (C.c_char_p, []),
+    "eegx_device_check": (C.c_int, []),
+    "eegx_normalize_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                     C.c_int64, C.c_void_p]),
+    "eegx_zscore_time_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
+    "eegx_dsp_plan_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int,
+                                       c_f32p, C.c_int, C.c_float, C.c_float]),
+    "eegx_dsp_plan_destroy": (C.c_int, [C.c_void_p]),
+    "eegx_dsp_plan_dims": (C.c_int, [C.c_void_p, c_int_p, c_int_p]),
+    "eegx_dsp_plan_kernel": (C.c_int, [C.c_void_p]),
+    "eegx_dsp_plan_force_generic": (C.c_int, [C.c_void_p, C.c_int]),
+    "eegx_dsp_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                   C.c_int64, C.c_void_p]),
+}
+
+
+class EegxError(RuntimeError):
+    """A libeegx entry point returned a negative status."""
+
+
+def lib():
+    """Load libeegx.so once; raise (loudly) if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EegxError(
+                f"{LIB_PATH} not found: the CUDA library is not built and there is no fallback "
+                "path. Run `python -m imagined_speech_translation_b200.build`.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().eegx_last_error().decode("utf-8", "replace")
+        raise EegxError(f"{what or 'libeegx'} failed with status {rc}: {msg}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None) as a void*."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(stream=None):
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)

@@ -1,0 +1,41 @@
+// Plan object of the fused DSP chain (opaque to C callers, see include/eegx.h).
+#pragma once
+#include "eegx_common.h"
+
+struct eegx_dsp_plan {
+    int C, T, n_fft, hop, numtaps;
+    int F, n_frames;
+    float log_eps, z_eps;
+    int device;
+    int kernel;          // 0 generic, 1 tuned (n_fft 256 / hop 64 / 65 taps / T % 64 == 0)
+    int force_generic;
+    // device tables, one allocation: taps[numtaps] | pad to 4 | window[n_fft] | twiddle float2[n_fft/2]
+    float* d_tables;
+    int off_window, off_twiddle, table_floats;
+    float h_taps[132];
+    size_t smem_generic;
+};
+
+namespace eegx {
+
+struct DspArgs {
+    const float* x;
+    const int64_t* onsets;
+    int64_t rec_len;
+    float* out;
+    int64_t rows;  // B * C
+    int C, T, n_fft, hop, numtaps, F, n_frames, log2_m;
+    float log_eps, z_eps;
+    const float* taps;     // device
+    const float* window;   // device
+    const float2* twiddle; // device, exp(-2*pi*i*k/n_fft), k < n_fft/2
+};
+
+int launch_dsp_generic(const eegx_dsp_plan* plan, const DspArgs& a, cudaStream_t st);
+size_t dsp_generic_smem_bytes(int T, int n_fft, int hop, int numtaps);
+
+// Tuned kernel for n_fft = 256, hop = 64, 65 taps (BASELINE config 2).
+bool dsp_tuned_supported(const eegx_dsp_plan* plan);
+int launch_dsp_tuned(const eegx_dsp_plan* plan, const DspArgs& a, cudaStream_t st);
+
+}  // namespace eegx

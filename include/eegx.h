@@ -1,0 +1,111 @@
+/*
+ * eegx.h -- C ABI of libeegx.so: the B200 (sm_100a) implementation of the
+ * EEG preprocessing + encoder hot path of alexsteinerr/imagined-speech-translation.
+ *
+ * The reference has no FFI / operator layer of its own;
+ * its boundary is the Python API of main_model/src.  Each entry point below
+ * therefore cites the reference *Python* code it replaces.  The Python classes
+ * in imagined_speech_translation_b200/ keep the reference signatures and call
+ * these functions through ctypes on tensor.data_ptr().
+ *
+ * Conventions (all entry points):
+ *   - return 0 on success, a negative eegx_status otherwise; the message is in
+ *     eegx_last_error() (thread-local).  No exceptions, no exit(), NO CPU
+ *     FALLBACK: on a device that is not sm_100 every compute call returns
+ *     EEGX_ERR_ARCH.
+ *   - every pointer except plans is DEVICE memory owned by the caller
+ *     (row-major, contiguous, float32 unless stated); inputs are const; outputs
+ *     must not alias inputs.
+ *   - work is enqueued asynchronously on `stream` (a cudaStream_t passed as
+ *     void*; NULL = legacy default stream); no host sync, no allocation inside
+ *     compute calls, so they are CUDA-graph capturable.
+ *   - plans own only O(KB) constant tables (FIR taps, window, twiddles).
+ */
+#ifndef EEGX_H
+#define EEGX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EEGX_VERSION 100 /* 0.1.0 */
+
+typedef enum eegx_status {
+    EEGX_OK = 0,
+    EEGX_ERR_ARCH = -1,      /* device is not compute capability 10.x */
+    EEGX_ERR_SHAPE = -2,     /* unsupported / inconsistent sizes */
+    EEGX_ERR_ALIGN = -3,     /* pointer not aligned as required */
+    EEGX_ERR_WORKSPACE = -4, /* workspace too small */
+    EEGX_ERR_CUDA = -5,      /* a CUDA runtime call failed */
+    EEGX_ERR_ARG = -6        /* NULL / invalid argument */
+} eegx_status;
+
+int eegx_version(void);
+const char* eegx_last_error(void);
+/* 0 if the current CUDA device can run this library (sm_100), else EEGX_ERR_ARCH. */
+int eegx_device_check(void);
+
+/* ------------------------------------------------------------------------
+ * Reference-actual normalisation.
+ * Replaces EEGDataset._process_raw_eeg + _normalize_eeg_sample
+ * (main_model/src/data/dataset.py:172-191, 193-225) for a whole batch:
+ *   v   = x[b, ch_idx[j], t]; nan -> 0, +inf -> 10, -inf -> -10
+ *   out = (v - center[j]) / scale[j]                (RobustScaler.transform)
+ * x: (B, C_in, T).  ch_idx/center/scale: (C_out,) device arrays (the four
+ * regions concatenated in the order frontal, temporal, central, parietal).
+ * Output addressing: channel j of trial b is written at
+ *   out + out_off[j] + b * out_bstride[j] + t
+ * so the four regions can land in four dense (B, C_r, T) buffers carved from
+ * one allocation.  out_off / out_bstride may both be NULL: dense (B, C_out, T).
+ * center/scale may both be NULL: only the gather + nan_to_num is applied.
+ * ------------------------------------------------------------------------ */
+int eegx_normalize_f32(const float* x, const int32_t* ch_idx, const float* center,
+                       const float* scale, float* out, const int64_t* out_off,
+                       const int64_t* out_bstride, int64_t B, int64_t C_in,
+                       int64_t C_out, int64_t T, void* stream);
+
+/* The scaler-less fallback branch of _normalize_eeg_sample (dataset.py:213-216):
+ * per (trial, channel) over time, population std: (v - mean_t) / (std_t + 1e-8),
+ * after the same gather + nan_to_num.  Same addressing as eegx_normalize_f32. */
+int eegx_zscore_time_f32(const float* x, const int32_t* ch_idx, float* out,
+                         const int64_t* out_off, const int64_t* out_bstride,
+                         int64_t B, int64_t C_in, int64_t C_out, int64_t T,
+                         void* stream);
+
+/* ------------------------------------------------------------------------
+ * north_star DSP chain (spec: SURVEY.md section 8(c); absent from the reference):
+ *   trial windowing -> band-pass FIR ("same", zero padded, delay compensated)
+ *   -> STFT (center=True, reflect pad, periodic Hann, one-sided)
+ *   -> log(|X|^2 + log_eps) -> per-(trial, channel) z-score over all F*N_f
+ *      values, population std, (L - mu) / (sigma + z_eps).
+ * One fused launch: x is read once, out is written once.
+ * ------------------------------------------------------------------------ */
+typedef struct eegx_dsp_plan eegx_dsp_plan;
+
+/* fir: HOST pointer to numtaps float32 taps (numtaps odd, <= 129).
+ * n_fft: power of two in [32, 2048]; T > n_fft/2; hop >= 1.
+ * Output dims: F = n_fft/2 + 1, N_f = 1 + T / hop. */
+int eegx_dsp_plan_create(eegx_dsp_plan** plan, int C, int T, int n_fft, int hop,
+                         const float* fir, int numtaps, float log_eps, float z_eps);
+int eegx_dsp_plan_destroy(eegx_dsp_plan* plan);
+int eegx_dsp_plan_dims(const eegx_dsp_plan* plan, int* F, int* N_f);
+/* Which kernel the plan dispatches to: 0 = generic, 1 = tuned n_fft=256/hop=64/K=65. */
+int eegx_dsp_plan_kernel(const eegx_dsp_plan* plan);
+/* Force the generic kernel (testing / A-B comparison). */
+int eegx_dsp_plan_force_generic(eegx_dsp_plan* plan, int on);
+
+/* onsets == NULL: x is (B, C, T), trials already cut.
+ * onsets != NULL: x is one continuous recording (C, rec_len) and
+ *                 trial b = x[:, onsets[b] : onsets[b] + T]  (int64 device array,
+ *                 every window must lie inside [0, rec_len)).
+ * out: (B, C, F, N_f) float32. */
+int eegx_dsp_forward(const eegx_dsp_plan* plan, const float* x, const int64_t* onsets,
+                     int64_t rec_len, float* out, int64_t B, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EEGX_H */

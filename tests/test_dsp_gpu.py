@@ -1,0 +1,141 @@
+"""GPU parity of the fused DSP chain (through the C ABI) against the golden
+spec vectors, the float64 oracle on seeded inputs, and size-independent
+properties at BASELINE config sizes.
+
+Tolerance (stated, SURVEY.md section 7 / north_star "<=1e-5 relative"):
+    max|a - b| / max|b| <= 1e-5   against the float64 oracle.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import imagined_speech_translation_b200 as pkg
+from oracle import preprocess_oracle as po
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def dsp(golden_dir):
+    return np.load(os.path.join(golden_dir, "dsp_spec.npz"))
+
+
+def _run(x_np, cfg=None, generic=False, taps=None):
+    B, C, T = x_np.shape
+    fe = pkg.SpectrogramFrontEnd(C, T, cfg, taps=taps)
+    if generic:
+        fe.force_generic(True)
+    out = fe(torch.from_numpy(x_np).cuda())
+    torch.cuda.synchronize()
+    return out.cpu().numpy(), fe
+
+
+@pytest.mark.parametrize("generic", [False, True])
+@pytest.mark.parametrize("key", ["a", "b", "c"])
+def test_golden_spec_vectors(dsp, key, generic):
+    n_fft, hop = (int(v) for v in dsp[f"cfg_{key}"])
+    got, fe = _run(dsp[f"x_{key}"], {"n_fft": n_fft, "hop": hop}, generic=generic)
+    assert got.shape == dsp[f"z_{key}"].shape
+    assert np.array_equal(fe.taps, dsp["taps"].astype(np.float32))
+    assert po.rel_max_err(got, dsp[f"z_{key}"]) <= TOL
+
+
+@pytest.mark.parametrize("generic", [False, True])
+@pytest.mark.parametrize("B,C,T,n_fft,hop", [
+    (3, 5, 2048, 256, 64),      # config-2 shape, small batch
+    (2, 3, 2000, 256, 64),      # T not a multiple of hop
+    (1, 1, 1651, 256, 64),      # the real-data length, odd
+    (2, 2, 4096, 1024, 256),    # config-4 long window
+    (2, 4, 512, 64, 16),
+    (1, 2, 300, 256, 100),      # hop does not divide n_fft
+])
+def test_vs_float64_oracle(B, C, T, n_fft, hop, generic):
+    x = po.synth_eeg(B, C, T, seed=B * 100 + T)
+    got, fe = _run(x, {"n_fft": n_fft, "hop": hop}, generic=generic)
+    ref = po.dsp_reference(x, fe.taps.astype(np.float64), n_fft=n_fft, hop=hop)
+    assert got.shape == ref.shape == (B, C, n_fft // 2 + 1, 1 + T // hop)
+    assert po.rel_max_err(got, ref) <= TOL
+
+
+def test_tuned_kernel_is_selected_for_config2():
+    fe = pkg.SpectrogramFrontEnd(64, 2048)
+    assert fe.kernel_name == "tuned"
+    fe2 = pkg.SpectrogramFrontEnd(8, 4096, pkg.DSP_CONFIG_LONG)
+    assert fe2.kernel_name in ("tuned", "generic")
+
+
+def test_tuned_and_generic_agree():
+    x = torch.from_numpy(po.synth_eeg(4, 64, 2048, seed=5)).cuda()
+    fe = pkg.SpectrogramFrontEnd(64, 2048)
+    a = fe(x).clone()
+    fe.force_generic(True)
+    b = fe(x)
+    assert po.rel_max_err(a.cpu().numpy(), b.cpu().numpy()) <= TOL
+
+
+def test_other_taps_and_identity_filter():
+    x = po.synth_eeg(2, 3, 1024, seed=9)
+    for taps in (np.array([1.0], dtype=np.float32),
+                 pkg.design_bandpass_fir(33, (4.0, 40.0), 256.0),
+                 pkg.design_bandpass_fir(129, (1.0, 45.0), 256.0)):
+        got, fe = _run(x, taps=taps)
+        ref = po.dsp_reference(x, taps.astype(np.float64))
+        assert po.rel_max_err(got, ref) <= TOL
+
+
+def test_windowed_mode_equals_cut_trials():
+    C, T, L = 6, 2048, 9000
+    rec = torch.from_numpy(po.synth_eeg(1, C, L, seed=3)[0]).cuda().contiguous()
+    onsets = torch.tensor([0, 64, 1001, 4097, L - T], dtype=torch.int64, device="cuda")
+    fe = pkg.SpectrogramFrontEnd(C, T)
+    cut = torch.stack([rec[:, o:o + T] for o in onsets.tolist()]).contiguous()
+    a = fe.from_recording(rec, onsets)
+    b = fe(cut)
+    assert torch.equal(a, b)
+
+
+def test_full_size_properties():
+    """BASELINE config 2 (256 x 64 x 2048): properties that need no oracle run."""
+    B, C, T = 256, 64, 2048
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    x = 20.0 * torch.randn(B, C, T, generator=g, device="cuda")
+    fe = pkg.SpectrogramFrontEnd(C, T)
+    z = fe(x)
+    assert z.shape == (B, C, 129, 33) and torch.isfinite(z).all()
+    flat = z.reshape(B * C, -1).double()
+    assert flat.mean(dim=1).abs().max().item() <= 1e-5          # z-score: mean 0
+    assert (flat.std(dim=1, unbiased=False) - 1.0).abs().max().item() <= 1e-5   # std 1
+    # determinism (bit-stable) and batch independence (no cross-trial state)
+    assert torch.equal(z, fe(x))
+    sub = fe(x[17:19].contiguous())
+    assert torch.equal(sub, z[17:19])
+    # spot-check a handful of rows against the oracle at full size
+    xs = x[[0, 255]][:, [0, 63]].cpu().numpy()
+    ref = po.dsp_reference(xs, fe.taps.astype(np.float64))
+    got = z[[0, 255]][:, [0, 63]].cpu().numpy()
+    assert po.rel_max_err(got, ref) <= TOL
+    # scale covariance breaks under log, but a sign flip must not change anything
+    assert torch.equal(fe(-x), z)
+
+
+def test_degenerate_inputs():
+    fe = pkg.SpectrogramFrontEnd(2, 2048)
+    z = fe(torch.zeros(1, 2, 2048, device="cuda"))
+    assert torch.equal(z, torch.zeros_like(z))           # log(0 + 1) = 0, sigma = 0 -> 0 / eps
+    empty = fe(torch.empty(0, 2, 2048, device="cuda"))
+    assert empty.shape == (0, 2, 129, 33)
+
+
+def test_shape_and_argument_errors():
+    with pytest.raises(pkg.EegxError):
+        pkg.SpectrogramFrontEnd(2, 100, {"n_fft": 256})          # T <= n_fft/2
+    with pytest.raises(pkg.EegxError):
+        pkg.SpectrogramFrontEnd(2, 2048, {"n_fft": 200})         # not a power of two
+    fe = pkg.SpectrogramFrontEnd(2, 2048)
+    with pytest.raises(ValueError):
+        fe(torch.zeros(1, 3, 2048, device="cuda"))
+    with pytest.raises(pkg.EegxError):
+        fe(torch.zeros(1, 2, 2048))
