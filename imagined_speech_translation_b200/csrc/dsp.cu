@@ -93,8 +93,9 @@ extern "C" int eegx_dsp_forward(const eegx_dsp_plan* plan, const float* x, const
                                 int64_t rec_len, float* out, int64_t B, void* stream) {
     EEGX_REQUIRE(plan, EEGX_ERR_ARG, "plan is NULL");
     if (int rc = eegx::require_sm100()) return rc;
-    EEGX_REQUIRE(x && out, EEGX_ERR_ARG, "x/out must not be NULL");
     EEGX_REQUIRE(B >= 0, EEGX_ERR_SHAPE, "B=%lld", (long long)B);
+    if (B == 0) return EEGX_OK;
+    EEGX_REQUIRE(x && out, EEGX_ERR_ARG, "x/out must not be NULL");
     EEGX_REQUIRE(onsets == nullptr || rec_len >= plan->T, EEGX_ERR_SHAPE,
                  "windowed mode needs rec_len (%lld) >= T (%d)", (long long)rec_len, plan->T);
     EEGX_REQUIRE(eegx::aligned16(x) && eegx::aligned16(out), EEGX_ERR_ALIGN,

@@ -147,7 +147,7 @@ zscore_time_kernel(const float* __restrict__ x, const int32_t* __restrict__ ch_i
 }
 
 int check_common(const float* x, float* out, int64_t B, int64_t C_in, int64_t C_out, int64_t T) {
-    EEGX_REQUIRE(x && out, EEGX_ERR_ARG, "x/out must not be NULL");
+    EEGX_REQUIRE(B == 0 || (x && out), EEGX_ERR_ARG, "x/out must not be NULL");
     EEGX_REQUIRE(B >= 0 && C_in > 0 && C_out > 0 && T > 0, EEGX_ERR_SHAPE,
                  "bad sizes B=%lld C_in=%lld C_out=%lld T=%lld", (long long)B, (long long)C_in,
                  (long long)C_out, (long long)T);
