@@ -27,6 +27,7 @@ extern "C" int eegx_dsp_plan_create(eegx_dsp_plan** out_plan, int C, int T, int 
     p->log_eps = log_eps; p->z_eps = z_eps;
     p->force_generic = 0;
     p->d_tables = nullptr;
+    p->d_lane_tables = nullptr;
     for (int i = 0; i < 132; ++i) p->h_taps[i] = i < numtaps ? fir[i] : 0.0f;
     p->smem_generic = eegx::dsp_generic_smem_bytes(T, n_fft, hop, numtaps);
     if (p->smem_generic > 227 * 1024) {
@@ -60,6 +61,19 @@ extern "C" int eegx_dsp_plan_create(eegx_dsp_plan** out_plan, int C, int T, int 
         return eegx::set_error(EEGX_ERR_CUDA, "cudaMemcpy(tables): %s", cudaGetErrorString(e));
     }
     p->kernel = eegx::dsp_tuned_supported(p) ? 1 : 0;
+    if (p->kernel == 1) {
+        std::vector<float> lt(eegx::dsp_tuned_table_floats());
+        eegx::dsp_tuned_fill_tables(lt.data());
+        e = cudaMalloc(&p->d_lane_tables, lt.size() * sizeof(float));
+        if (e == cudaSuccess)
+            e = cudaMemcpy(p->d_lane_tables, lt.data(), lt.size() * sizeof(float), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            if (p->d_lane_tables) cudaFree(p->d_lane_tables);
+            cudaFree(p->d_tables);
+            delete p;
+            return eegx::set_error(EEGX_ERR_CUDA, "tuned tables: %s", cudaGetErrorString(e));
+        }
+    }
     *out_plan = p;
     return EEGX_OK;
 }
@@ -67,6 +81,7 @@ extern "C" int eegx_dsp_plan_create(eegx_dsp_plan** out_plan, int C, int T, int 
 extern "C" int eegx_dsp_plan_destroy(eegx_dsp_plan* plan) {
     if (!plan) return EEGX_OK;
     if (plan->d_tables) cudaFree(plan->d_tables);
+    if (plan->d_lane_tables) cudaFree(plan->d_lane_tables);
     delete plan;
     return EEGX_OK;
 }
@@ -119,6 +134,8 @@ extern "C" int eegx_dsp_forward(const eegx_dsp_plan* plan, const float* x, const
     a.window = plan->d_tables + plan->off_window;
     a.twiddle = reinterpret_cast<const float2*>(plan->d_tables + plan->off_twiddle);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (plan->kernel == 1 && !plan->force_generic) return eegx::launch_dsp_tuned(plan, a, st);
+    // windowed mode (arbitrary, possibly unaligned onsets) always takes the generic kernel
+    if (plan->kernel == 1 && !plan->force_generic && onsets == nullptr)
+        return eegx::launch_dsp_tuned(plan, a, st);
     return eegx::launch_dsp_generic(plan, a, st);
 }

@@ -11,6 +11,7 @@ struct eegx_dsp_plan {
     int force_generic;
     // device tables, one allocation: taps[numtaps] | pad to 4 | window[n_fft] | twiddle float2[n_fft/2]
     float* d_tables;
+    float* d_lane_tables;  // tuned kernel only: [8][60] per-lane window / twiddle constants
     int off_window, off_twiddle, table_floats;
     float h_taps[132];
     size_t smem_generic;
@@ -37,5 +38,7 @@ size_t dsp_generic_smem_bytes(int T, int n_fft, int hop, int numtaps);
 // Tuned kernel for n_fft = 256, hop = 64, 65 taps (BASELINE config 2).
 bool dsp_tuned_supported(const eegx_dsp_plan* plan);
 int launch_dsp_tuned(const eegx_dsp_plan* plan, const DspArgs& a, cudaStream_t st);
+int dsp_tuned_table_floats();
+void dsp_tuned_fill_tables(float* host);
 
 }  // namespace eegx

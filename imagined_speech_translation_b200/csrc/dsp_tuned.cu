@@ -1,12 +1,468 @@
-// Tuned DSP kernel for BASELINE config 2 (n_fft 256 / hop 64 / 65 taps).
+// Tuned fused DSP kernel for BASELINE config 2: T = 2048, 65-tap FIR, n_fft = 256, hop = 64.
+//
+//   x (rows, 2048) f32  ->  out (rows, 129, 33) f32,   rows = B * C
+//
+// Spec: SURVEY.md section 8(c) (the reference has no DSP code; dsp_generic.cu is the
+// any-shape implementation of the same spec and the two are cross-checked on the GPU).
+//
+// Design.  Persistent CTAs, two per SM, 192 threads (6 warps) each;
+// one tile = 2 consecutive rows per iteration:
+//
+//   load   TMA: one cp.async.bulk (global -> shared, 8 KB) per row, completion on an
+//          mbarrier, issued one tile ahead so it overlaps the STFT phase of the current
+//          tile.  The zero halos the FIR needs are written once per CTA.
+//   FIR    register-tiled direct form: a thread owns 8 consecutive outputs, streams the 72
+//          inputs it needs through 18 LDS.128 and issues 520 FFMAs with the taps as
+//          constant-bank operands.  Lanes alternate between the two rows and the row pitch
+//          is 16 bytes off a multiple of 128, which makes those loads bank-conflict free in
+//          a dense layout.  Outputs go to a reflect-extended row in shared memory, so the
+//          STFT needs no boundary logic.
+//   STFT   8 lanes per frame.  Real FFT-256 = complex FFT-128 on z[n] = y[2n] + i*y[2n+1]
+//          = (8 lanes x two radix-8 FFTs in registers) -> twiddle -> 8x16 transpose through
+//          an XOR-swizzled 1 KB shared-memory patch (conflict-free 128-bit accesses)
+//          -> one 16-point FFT per lane.  The conjugate pairing Z[k] <-> Z[128-k] of the
+//          split step lives in lanes g and 8-g: 16 warp shuffles per lane.  Power, log
+//          (MUFU lg2) and the partial sums for the z-score are taken in registers.
+//   stats  264 per-lane partials per row are combined in a fixed order in fp64 by one warp
+//          per row (bit-stable, no atomics).
+//   store  each row leaves as coalesced 128-bit streaming stores (the row is placed in
+//          shared memory with the same 16-byte phase as its global address).
+//
+// Algorithmic HBM bytes per row: 8192 read + 17028 written; nothing else touches HBM.
+#include <math.h>
+
 #include "dsp_plan.h"
+
+namespace {
+
+constexpr int T = 2048;
+constexpr int NF = 33;
+constexpr int F = 129;
+constexpr int ROW_OUT = F * NF;          // 4257
+constexpr int ROWS = 2;                  // rows per tile
+constexpr int NT = 192;                  // 6 warps
+constexpr int NWARPS = NT / 32;
+constexpr int NGROUPS = NT / 8;          // 24 groups of 8 lanes
+constexpr int XS_PITCH = 32 + T + 32 + 4;   // floats; 8464 B = 66 * 128 + 16
+constexpr int YS_PITCH = 128 + T + 128 + 4; // floats; 9232 B = 72 * 128 + 16
+constexpr int LS_PITCH = 4264;           // >= 4257 + 3, multiple of 4
+constexpr int LANE_TABLE = 60;           // floats of per-lane constants
+constexpr int NTASKS = 17;               // warp-tasks per tile: 2 rows x 8 + 1 leftover (m = 32)
+
+constexpr int OFF_XS = 0;
+constexpr int OFF_YS = OFF_XS + ROWS * XS_PITCH;
+constexpr int OFF_LS = OFF_YS + ROWS * YS_PITCH;
+constexpr int OFF_SCR = OFF_LS + ROWS * LS_PITCH;
+constexpr int OFF_STAT = OFF_SCR + NGROUPS * 256;
+constexpr int OFF_ROWSTAT = OFF_STAT + ROWS * NF * 8 * 2;
+constexpr int OFF_BAR = OFF_ROWSTAT + 2 * ROWS;       // 8-byte mbarrier
+constexpr int SMEM_FLOATS = OFF_BAR + 2;
+constexpr size_t SMEM_BYTES = SMEM_FLOATS * sizeof(float);
+static_assert(2 * (SMEM_BYTES + 1024) <= 227 * 1024, "two CTAs per SM must fit");
+static_assert((OFF_YS % 4) == 0 && (OFF_LS % 4) == 0 && (OFF_SCR % 4) == 0 && (OFF_STAT % 2) == 0 &&
+              (OFF_BAR % 2) == 0, "alignment of the shared-memory regions");
+
+struct TunedArgs {
+    const float* x;
+    float* out;
+    long long rows;
+    const float* lane_tables;  // [8][LANE_TABLE]
+    float log_eps4;            // 4 * log_eps (the FFT is kept scaled by 2)
+    float z_eps;
+    float taps_rev[65];        // taps_rev[d] = h[64 - d]
+};
+
+struct cf { float r, i; };
+__device__ __forceinline__ cf cadd(cf a, cf b) { return {a.r + b.r, a.i + b.i}; }
+__device__ __forceinline__ cf csub(cf a, cf b) { return {a.r - b.r, a.i - b.i}; }
+__device__ __forceinline__ cf cmul(cf a, float wr, float wi) {
+    return {fmaf(a.r, wr, -a.i * wi), fmaf(a.r, wi, a.i * wr)};
+}
+__device__ __forceinline__ cf mul_neg_i(cf a) { return {a.i, -a.r}; }   // a * (-i)
+
+constexpr float RSQRT2 = 0.70710678118654752440f;
+
+// In-place forward 8-point FFT (e^{-i...}), natural order in and out.
+__device__ __forceinline__ void fft8(cf (&v)[8]) {
+    // radix-2 DIF split: evens from sums, odds from twiddled differences
+    cf e0 = cadd(v[0], v[4]), e1 = cadd(v[1], v[5]), e2 = cadd(v[2], v[6]), e3 = cadd(v[3], v[7]);
+    cf d0 = csub(v[0], v[4]), d1 = csub(v[1], v[5]), d2 = csub(v[2], v[6]), d3 = csub(v[3], v[7]);
+    cf o0 = d0;
+    cf o1 = {(d1.r + d1.i) * RSQRT2, (d1.i - d1.r) * RSQRT2};     // * W8^1
+    cf o2 = mul_neg_i(d2);                                         // * W8^2
+    cf o3 = {(d3.i - d3.r) * RSQRT2, -(d3.r + d3.i) * RSQRT2};    // * W8^3
+    // 4-point FFTs
+    cf s0 = cadd(e0, e2), s1 = csub(e0, e2), s2 = cadd(e1, e3), s3 = mul_neg_i(csub(e1, e3));
+    v[0] = cadd(s0, s2); v[4] = csub(s0, s2); v[2] = cadd(s1, s3); v[6] = csub(s1, s3);
+    cf t0 = cadd(o0, o2), t1 = csub(o0, o2), t2 = cadd(o1, o3), t3 = mul_neg_i(csub(o1, o3));
+    v[1] = cadd(t0, t2); v[5] = csub(t0, t2); v[3] = cadd(t1, t3); v[7] = csub(t1, t3);
+}
+
+// Forward 16-point FFT, natural order in and out.
+__device__ __forceinline__ void fft16(const cf (&c)[16], cf (&out)[16]) {
+    constexpr float C1 = 0.92387953251128675613f, S1 = 0.38268343236508977173f;  // cos/sin(pi/8)
+    cf e[8], o[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+        e[n] = cadd(c[n], c[n + 8]);
+        o[n] = csub(c[n], c[n + 8]);
+    }
+    // o[n] *= W16^n
+    o[1] = cmul(o[1], C1, -S1);
+    o[2] = {(o[2].r + o[2].i) * RSQRT2, (o[2].i - o[2].r) * RSQRT2};
+    o[3] = cmul(o[3], S1, -C1);
+    o[4] = mul_neg_i(o[4]);
+    o[5] = cmul(o[5], -S1, -C1);
+    o[6] = {(o[6].i - o[6].r) * RSQRT2, -(o[6].r + o[6].i) * RSQRT2};
+    o[7] = cmul(o[7], -C1, -S1);
+    fft8(e);
+    fft8(o);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        out[2 * k] = e[k];
+        out[2 * k + 1] = o[k];
+    }
+}
+
+__device__ __forceinline__ float fast_log2(float x) {   // x >= 4*log_eps > 0: no denormal path
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// ---- TMA (1-D bulk copy) + mbarrier helpers ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra.uni WAIT_DONE;\n\t"
+        "bra.uni WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+
+
+__device__ __forceinline__ void issue_tile_loads(const TunedArgs& a, float* xs, unsigned bar, long long row0) {
+    // one thread: arm the barrier with the byte count, then one bulk copy per row
+    const int nrows = (a.rows - row0) < ROWS ? (int)(a.rows - row0) : ROWS;
+    mbar_expect_tx(bar, (unsigned)(nrows * T * sizeof(float)));
+    for (int r = 0; r < nrows; ++r)
+        tma_load_1d(smem_u32(xs + r * XS_PITCH + 32), a.x + (row0 + r) * (long long)T,
+                    (unsigned)(T * sizeof(float)), bar);
+}
+
+__global__ void __launch_bounds__(NT, 2) dsp_tuned_kernel(const __grid_constant__ TunedArgs a) {
+    extern __shared__ __align__(128) float smem[];
+    float* xs = smem + OFF_XS;
+    float* ys = smem + OFF_YS;
+    float* Ls = smem + OFF_LS;
+    float* scr = smem + OFF_SCR;
+    float2* stat = reinterpret_cast<float2*>(smem + OFF_STAT);
+    float* rowstat = smem + OFF_ROWSTAT;
+    const unsigned bar = smem_u32(smem + OFF_BAR);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = tid & 7, q = (tid >> 3) & 3;
+
+    // per-lane constants (fixed for the lifetime of the CTA)
+    float win[16], twr[2][7], twi[2][7], spr[8], spi[8];
+    {
+        const float* tb = a.lane_tables + g * LANE_TABLE;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) win[i] = __ldg(tb + i);
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                twr[e][k] = __ldg(tb + 16 + (e * 7 + k) * 2);
+                twi[e][k] = __ldg(tb + 16 + (e * 7 + k) * 2 + 1);
+            }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            spr[k] = __ldg(tb + 44 + 2 * k);
+            spi[k] = __ldg(tb + 44 + 2 * k + 1);
+        }
+    }
+
+    // FIR zero halos (32 samples each side of every row), written once.
+    for (int i = tid; i < ROWS * 64; i += NT) {
+        const int r = i >> 6, h = i & 63;
+        xs[r * XS_PITCH + (h < 32 ? h : T + h)] = 0.0f;
+    }
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const long long ntiles = (a.rows + ROWS - 1) / ROWS;
+    long long tile = blockIdx.x;
+    if (tile < ntiles && tid == 0) issue_tile_loads(a, xs, bar, tile * ROWS);
+    unsigned phase = 0;
+
+    for (; tile < ntiles; tile += gridDim.x) {
+        const long long row0 = tile * ROWS;
+        mbar_wait(bar, phase);
+        phase ^= 1;
+
+        // ------------------------------ FIR ------------------------------
+        // lanes alternate rows; a thread owns outputs t = 8j .. 8j+7 of its row
+        for (int th = tid; th < ROWS * 256; th += NT) {
+            const int r = th & 1, j = th >> 1;
+            const float4* src = reinterpret_cast<const float4*>(xs + r * XS_PITCH) + 2 * j;
+            float acc[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+#pragma unroll
+            for (int sl = 0; sl < 18; ++sl) {
+                const float4 v = src[sl];
+                const float in[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = 4 * sl + u;   // input i feeds output e with tap d = i - e
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int d = i - e;
+                        if (d >= 0 && d <= 64) acc[e] = fmaf(a.taps_rev[d], in[u], acc[e]);
+                    }
+                }
+            }
+            float* yrow = ys + r * YS_PITCH;
+            float4* dsty = reinterpret_cast<float4*>(yrow + 128 + 8 * j);
+            dsty[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            dsty[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            if (j <= 16) {          // reflect copy on the left: index -t for t in [1, 128]
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int t = 8 * j + e;
+                    if (t >= 1 && t <= 128) yrow[128 - t] = acc[e];
+                }
+            }
+            if (j >= 239) {         // reflect copy on the right: index 2(T-1)-t for t in [T-129, T-2]
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int t = 8 * j + e;
+                    if (t >= T - 129 && t <= T - 2) yrow[2 * (T - 1) - t + 128] = acc[e];
+                }
+            }
+        }
+        __syncthreads();
+        // xs is free again: fetch the next tile while the STFT runs
+        if (tid == 0 && tile + gridDim.x < ntiles) issue_tile_loads(a, xs, bar, (tile + gridDim.x) * ROWS);
+
+        // ------------------------------ STFT ------------------------------
+        // rows sit in Ls with the same 16-byte phase as their global address
+        float* myscr = scr + (tid >> 3) * 256;
+#pragma unroll 1
+        for (int round = 0; round < 3; ++round) {
+            const int task = warp + NWARPS * round;          // 0..17
+            if (task >= NTASKS) break;                       // warp-uniform
+            // tasks 0..15: row = task / 8, frames (task % 8) + 8 q;  task 16: frame 32 of row q
+            const bool full = task < 16;
+            const bool valid = full || q < ROWS;
+            const int r = full ? (task >> 3) : (q & (ROWS - 1));
+            const int m = full ? (task & 7) + 8 * q : 32;
+            const float* yseg = ys + r * YS_PITCH + m * 64;  // extended position 64 m
+
+            cf z0[8], z1[8];
+#pragma unroll
+            for (int aa = 0; aa < 8; ++aa) {
+                const float4 u = *reinterpret_cast<const float4*>(yseg + aa * 32 + 4 * g);
+                float v0, v1, v2, v3;
+                if (aa < 4) {
+                    v0 = u.x * win[aa * 4 + 0]; v1 = u.y * win[aa * 4 + 1];
+                    v2 = u.z * win[aa * 4 + 2]; v3 = u.w * win[aa * 4 + 3];
+                } else {   // hann[n + 128] = 1 - hann[n]
+                    v0 = fmaf(-u.x, win[(aa - 4) * 4 + 0], u.x); v1 = fmaf(-u.y, win[(aa - 4) * 4 + 1], u.y);
+                    v2 = fmaf(-u.z, win[(aa - 4) * 4 + 2], u.z); v3 = fmaf(-u.w, win[(aa - 4) * 4 + 3], u.w);
+                }
+                z0[aa] = {v0, v1};
+                z1[aa] = {v2, v3};
+            }
+            fft8(z0);
+            fft8(z1);
+#pragma unroll
+            for (int k = 1; k < 8; ++k) {
+                z0[k] = cmul(z0[k], twr[0][k - 1], twi[0][k - 1]);
+                z1[k] = cmul(z1[k], twr[1][k - 1], twi[1][k - 1]);
+            }
+            // 8 x 16 transpose through the group's swizzled patch
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                *reinterpret_cast<float4*>(myscr + k * 32 + ((g ^ k) << 2)) =
+                    make_float4(z0[k].r, z0[k].i, z1[k].r, z1[k].i);
+            __syncwarp();
+            cf bb[16], Z[16];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const float4 v = *reinterpret_cast<const float4*>(myscr + g * 32 + ((jj ^ g) << 2));
+                bb[2 * jj] = {v.x, v.y};
+                bb[2 * jj + 1] = {v.z, v.w};
+            }
+            fft16(bb, Z);   // Z[k2] = Zc[g + 8 k2]
+
+            // conjugate partner: lane (8 - g) & 7 of the same group, index 15 - k2
+            // (lane 0 pairs with itself at 16 - k2, so as a source it sends a rotated copy)
+            const int src_lane = (lane & 24) | ((8 - g) & 7);
+            cf R[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const cf own = Z[8 + jj];
+                const cf rot = Z[(9 + jj) & 15];
+                const float sr = g == 0 ? rot.r : own.r;
+                const float si = g == 0 ? rot.i : own.i;
+                R[jj].r = __shfl_sync(0xffffffffu, sr, src_lane);
+                R[jj].i = __shfl_sync(0xffffffffu, si, src_lane);
+            }
+            float* Lrow = Ls + r * LS_PITCH + (int)((row0 + r) & 3) + m;
+            float s1 = 0.0f, s2 = 0.0f;
+            constexpr float LN2 = 0.69314718055994530942f;
+            if (valid) {
+#pragma unroll
+                for (int k2 = 0; k2 < 8; ++k2) {
+                    const cf zk = Z[k2], zm = R[7 - k2];                     // R[j - 8] holds index j
+                    const cf E = {zk.r + zm.r, zk.i - zm.i};
+                    const cf D = {zk.r - zm.r, zk.i + zm.i};
+                    const cf O = {D.i, -D.r};
+                    const cf Tt = cmul(O, spr[k2], spi[k2]);
+                    const cf A = cadd(E, Tt), Bc = csub(E, Tt);
+                    const float pa = fmaf(A.r, A.r, fmaf(A.i, A.i, a.log_eps4));
+                    const float pb = fmaf(Bc.r, Bc.r, fmaf(Bc.i, Bc.i, a.log_eps4));
+                    const float la = fmaf(fast_log2(pa), LN2, -2.0f * LN2);
+                    const float lb = fmaf(fast_log2(pb), LN2, -2.0f * LN2);
+                    Lrow[(g + 8 * k2) * NF] = la;
+                    Lrow[(128 - g - 8 * k2) * NF] = lb;
+                    s1 += la + lb;
+                    s2 = fmaf(la, la, fmaf(lb, lb, s2));
+                }
+                if (g == 0) {   // bin 64 pairs with itself: |X[64]|^2 = |Zc[64]|^2
+                    const cf zz = Z[8];
+                    const float p = fmaf(4.0f * zz.r, zz.r, fmaf(4.0f * zz.i, zz.i, a.log_eps4));
+                    const float l = fmaf(fast_log2(p), LN2, -2.0f * LN2);
+                    Lrow[64 * NF] = l;
+                    s1 += l;
+                    s2 = fmaf(l, l, s2);
+                }
+                stat[(r * NF + m) * 8 + g] = make_float2(s1, s2);
+            }
+        }
+        __syncthreads();
+
+        // ------------------------------ row statistics ------------------------------
+        if (warp < ROWS) {
+            double d1 = 0.0, d2 = 0.0;
+            for (int i = lane; i < NF * 8; i += 32) {
+                const float2 p = stat[warp * NF * 8 + i];
+                d1 += (double)p.x;
+                d2 += (double)p.y;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+                d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+            }
+            if (lane == 0) {
+                const double mean = d1 / (double)ROW_OUT;
+                double var = d2 / (double)ROW_OUT - mean * mean;
+                var = var > 0.0 ? var : 0.0;
+                const float inv = (float)(1.0 / (sqrt(var) + (double)a.z_eps));
+                rowstat[2 * warp] = inv;
+                rowstat[2 * warp + 1] = (float)(-mean) * inv;
+            }
+        }
+        __syncthreads();
+
+        // ------------------------------ normalise + store ------------------------------
+        const int nrows = (a.rows - row0) < ROWS ? (int)(a.rows - row0) : ROWS;
+        for (int r = 0; r < nrows; ++r) {
+            const int ph = (int)((row0 + r) & 3);            // float phase of the global row start
+            const float* src = Ls + r * LS_PITCH + ph;
+            float* dst = a.out + (row0 + r) * (long long)ROW_OUT;
+            const float inv = rowstat[2 * r], c = rowstat[2 * r + 1];
+            const int head = (4 - ph) & 3;
+            const int n4 = (ROW_OUT - head) >> 2;
+            const int tail = ROW_OUT - head - 4 * n4;
+            const float4* s4 = reinterpret_cast<const float4*>(src + head);
+            float4* d4 = reinterpret_cast<float4*>(dst + head);
+            for (int v = tid; v < n4; v += NT) {
+                const float4 l = s4[v];
+                __stcs(d4 + v, make_float4(fmaf(l.x, inv, c), fmaf(l.y, inv, c), fmaf(l.z, inv, c),
+                                           fmaf(l.w, inv, c)));
+            }
+            if (tid < head) __stcs(dst + tid, fmaf(src[tid], inv, c));
+            if (tid < tail) __stcs(dst + head + 4 * n4 + tid, fmaf(src[head + 4 * n4 + tid], inv, c));
+        }
+        // The post-FIR barrier of the next iteration orders these reads of Ls / rowstat against
+        // the next tile's STFT writes.
+    }
+}
+
+// per-lane constant tables, computed in double
+void fill_lane_tables(float* t) {
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int g = 0; g < 8; ++g) {
+        float* tb = t + g * LANE_TABLE;
+        for (int aa = 0; aa < 4; ++aa)
+            for (int e = 0; e < 4; ++e) {
+                const int n = 32 * aa + 4 * g + e;
+                tb[aa * 4 + e] = (float)(0.5 - 0.5 * cos(two_pi * n / 256.0));
+            }
+        for (int e = 0; e < 2; ++e)
+            for (int k = 1; k < 8; ++k) {
+                const double ang = -two_pi * (double)((2 * g + e) * k) / 128.0;
+                tb[16 + (e * 7 + (k - 1)) * 2] = (float)cos(ang);
+                tb[16 + (e * 7 + (k - 1)) * 2 + 1] = (float)sin(ang);
+            }
+        for (int k2 = 0; k2 < 8; ++k2) {
+            const double ang = -two_pi * (double)(g + 8 * k2) / 256.0;
+            tb[44 + 2 * k2] = (float)cos(ang);
+            tb[44 + 2 * k2 + 1] = (float)sin(ang);
+        }
+    }
+}
+
+}  // namespace
 
 namespace eegx {
 
-bool dsp_tuned_supported(const eegx_dsp_plan*) { return false; }
+bool dsp_tuned_supported(const eegx_dsp_plan* p) {
+    return p->n_fft == 256 && p->hop == 64 && p->numtaps == 65 && p->T == T;
+}
 
-int launch_dsp_tuned(const eegx_dsp_plan*, const DspArgs&, cudaStream_t) {
-    return set_error(EEGX_ERR_SHAPE, "tuned DSP kernel not available for this plan");
+int dsp_tuned_table_floats() { return 8 * LANE_TABLE; }
+void dsp_tuned_fill_tables(float* host) { fill_lane_tables(host); }
+
+int launch_dsp_tuned(const eegx_dsp_plan* plan, const DspArgs& d, cudaStream_t st) {
+    EEGX_REQUIRE(d.onsets == nullptr, EEGX_ERR_ARG, "tuned kernel takes pre-cut trials only");
+    EEGX_REQUIRE(plan->d_lane_tables != nullptr, EEGX_ERR_ARG, "plan has no tuned tables");
+    TunedArgs a;
+    a.x = d.x;
+    a.out = d.out;
+    a.rows = d.rows;
+    a.lane_tables = plan->d_lane_tables;
+    a.log_eps4 = 4.0f * plan->log_eps;
+    a.z_eps = plan->z_eps;
+    for (int i = 0; i < 65; ++i) a.taps_rev[i] = plan->h_taps[64 - i];
+    EEGX_CUDA_CHECK(cudaFuncSetAttribute(dsp_tuned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)SMEM_BYTES));
+    const long long ntiles = (d.rows + ROWS - 1) / ROWS;
+    const long long max_ctas = 2LL * kNumSMsB200;
+    const int grid = (int)(ntiles < max_ctas ? ntiles : max_ctas);
+    dsp_tuned_kernel<<<grid, NT, SMEM_BYTES, st>>>(a);
+    EEGX_CUDA_CHECK(cudaGetLastError());
+    return EEGX_OK;
 }
 
 }  // namespace eegx
