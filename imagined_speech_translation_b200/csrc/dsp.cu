@@ -1,5 +1,6 @@
 // Plan management and dispatch of the fused DSP chain (C ABI, include/eegx.h).
 #include <math.h>
+#include <stdlib.h>
 #include <new>
 #include <vector>
 
@@ -26,6 +27,10 @@ extern "C" int eegx_dsp_plan_create(eegx_dsp_plan** out_plan, int C, int T, int 
     p->n_frames = 1 + T / hop;
     p->log_eps = log_eps; p->z_eps = z_eps;
     p->force_generic = 0;
+    {
+        const char* v = getenv("EEGX_DSP_VARIANT");
+        p->tuned_variant = v ? atoi(v) : 0;
+    }
     p->d_tables = nullptr;
     p->d_lane_tables = nullptr;
     for (int i = 0; i < 132; ++i) p->h_taps[i] = i < numtaps ? fir[i] : 0.0f;

@@ -9,6 +9,7 @@ struct eegx_dsp_plan {
     int device;
     int kernel;          // 0 generic, 1 tuned (n_fft 256 / hop 64 / 65 taps / T % 64 == 0)
     int force_generic;
+    int tuned_variant;   // tile shape of the tuned kernel (EEGX_DSP_VARIANT, default 0 = auto)
     // device tables, one allocation: taps[numtaps] | pad to 4 | window[n_fft] | twiddle float2[n_fft/2]
     float* d_tables;
     float* d_lane_tables;  // tuned kernel only: [8][60] per-lane window / twiddle constants

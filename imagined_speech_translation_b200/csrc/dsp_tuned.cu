@@ -5,8 +5,9 @@
 // Spec: SURVEY.md section 8(c) (the reference has no DSP code; dsp_generic.cu is the
 // any-shape implementation of the same spec and the two are cross-checked on the GPU).
 //
-// Design.  Persistent CTAs, two per SM, 192 threads (6 warps) each;
-// one tile = 2 consecutive rows per iteration:
+// Design.  Persistent CTAs; a tile is ROWS consecutive rows per
+// iteration.  Default: 1 row per tile, 96 threads, four CTAs per SM (measured faster than
+// 2 rows / 192 threads / two CTAs per SM: more independent CTAs hide each other's barriers):
 //
 //   load   TMA: one cp.async.bulk (global -> shared, 8 KB) per row, completion on an
 //          mbarrier, issued one tile ahead so it overlaps the STFT phase of the current
@@ -39,28 +40,33 @@ constexpr int T = 2048;
 constexpr int NF = 33;
 constexpr int F = 129;
 constexpr int ROW_OUT = F * NF;          // 4257
-constexpr int ROWS = 2;                  // rows per tile
-constexpr int NT = 192;                  // 6 warps
-constexpr int NWARPS = NT / 32;
-constexpr int NGROUPS = NT / 8;          // 24 groups of 8 lanes
 constexpr int XS_PITCH = 32 + T + 32 + 4;   // floats; 8464 B = 66 * 128 + 16
 constexpr int YS_PITCH = 128 + T + 128 + 4; // floats; 9232 B = 72 * 128 + 16
 constexpr int LS_PITCH = 4264;           // >= 4257 + 3, multiple of 4
 constexpr int LANE_TABLE = 60;           // floats of per-lane constants
-constexpr int NTASKS = 17;               // warp-tasks per tile: 2 rows x 8 + 1 leftover (m = 32)
 
-constexpr int OFF_XS = 0;
-constexpr int OFF_YS = OFF_XS + ROWS * XS_PITCH;
-constexpr int OFF_LS = OFF_YS + ROWS * YS_PITCH;
-constexpr int OFF_SCR = OFF_LS + ROWS * LS_PITCH;
-constexpr int OFF_STAT = OFF_SCR + NGROUPS * 256;
-constexpr int OFF_ROWSTAT = OFF_STAT + ROWS * NF * 8 * 2;
-constexpr int OFF_BAR = OFF_ROWSTAT + 2 * ROWS;       // 8-byte mbarrier
-constexpr int SMEM_FLOATS = OFF_BAR + 2;
-constexpr size_t SMEM_BYTES = SMEM_FLOATS * sizeof(float);
-static_assert(2 * (SMEM_BYTES + 1024) <= 227 * 1024, "two CTAs per SM must fit");
-static_assert((OFF_YS % 4) == 0 && (OFF_LS % 4) == 0 && (OFF_SCR % 4) == 0 && (OFF_STAT % 2) == 0 &&
-              (OFF_BAR % 2) == 0, "alignment of the shared-memory regions");
+// Shared-memory carve-up for a tile of ROWS rows processed by NT threads.
+template <int ROWS, int NT>
+struct Cfg {
+    static constexpr int NWARPS = NT / 32;
+    static constexpr int NGROUPS = NT / 8;              // groups of 8 lanes (one frame each)
+    static constexpr int NTASKS = 8 * ROWS + 1;         // warp-tasks per tile: 8 per row + leftover (m = 32)
+    static constexpr int ROUNDS = (NTASKS + NWARPS - 1) / NWARPS;
+    static constexpr int OFF_XS = 0;
+    static constexpr int OFF_YS = OFF_XS + ROWS * XS_PITCH;
+    static constexpr int OFF_LS = OFF_YS + ROWS * YS_PITCH;
+    static constexpr int OFF_SCR = OFF_LS + ROWS * LS_PITCH;
+    static constexpr int OFF_STAT = OFF_SCR + NGROUPS * 256;
+    static constexpr int OFF_BAR = OFF_STAT + ROWS * NF * 8 * 2;   // 8-byte mbarrier
+    static constexpr int SMEM_FLOATS = OFF_BAR + 2;
+    static constexpr size_t SMEM_BYTES = SMEM_FLOATS * sizeof(float);
+    static constexpr int CTAS_PER_SM = (int)((227 * 1024) / (SMEM_BYTES + 1024)) < (65536 / (NT * 168))
+                                           ? (int)((227 * 1024) / (SMEM_BYTES + 1024))
+                                           : (65536 / (NT * 168));
+    static_assert((OFF_YS % 4) == 0 && (OFF_LS % 4) == 0 && (OFF_SCR % 4) == 0 && (OFF_STAT % 2) == 0 &&
+                  (OFF_BAR % 2) == 0, "alignment of the shared-memory regions");
+    static_assert(CTAS_PER_SM >= 1, "tile does not fit");
+};
 
 struct TunedArgs {
     const float* x;
@@ -153,6 +159,7 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
 }
 
 
+template <int ROWS>
 __device__ __forceinline__ void issue_tile_loads(const TunedArgs& a, float* xs, unsigned bar, long long row0) {
     // one thread: arm the barrier with the byte count, then one bulk copy per row
     const int nrows = (a.rows - row0) < ROWS ? (int)(a.rows - row0) : ROWS;
@@ -162,15 +169,18 @@ __device__ __forceinline__ void issue_tile_loads(const TunedArgs& a, float* xs, 
                     (unsigned)(T * sizeof(float)), bar);
 }
 
-__global__ void __launch_bounds__(NT, 2) dsp_tuned_kernel(const __grid_constant__ TunedArgs a) {
+template <int ROWS, int NT>
+__global__ void __launch_bounds__(NT, Cfg<ROWS, NT>::CTAS_PER_SM)
+dsp_tuned_kernel(const __grid_constant__ TunedArgs a) {
+    using C = Cfg<ROWS, NT>;
+    constexpr int NWARPS = C::NWARPS;
     extern __shared__ __align__(128) float smem[];
-    float* xs = smem + OFF_XS;
-    float* ys = smem + OFF_YS;
-    float* Ls = smem + OFF_LS;
-    float* scr = smem + OFF_SCR;
-    float2* stat = reinterpret_cast<float2*>(smem + OFF_STAT);
-    float* rowstat = smem + OFF_ROWSTAT;
-    const unsigned bar = smem_u32(smem + OFF_BAR);
+    float* xs = smem + C::OFF_XS;
+    float* ys = smem + C::OFF_YS;
+    float* Ls = smem + C::OFF_LS;
+    float* scr = smem + C::OFF_SCR;
+    float2* stat = reinterpret_cast<float2*>(smem + C::OFF_STAT);
+    const unsigned bar = smem_u32(smem + C::OFF_BAR);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = tid & 7, q = (tid >> 3) & 3;
@@ -208,7 +218,7 @@ __global__ void __launch_bounds__(NT, 2) dsp_tuned_kernel(const __grid_constant_
 
     const long long ntiles = (a.rows + ROWS - 1) / ROWS;
     long long tile = blockIdx.x;
-    if (tile < ntiles && tid == 0) issue_tile_loads(a, xs, bar, tile * ROWS);
+    if (tile < ntiles && tid == 0) issue_tile_loads<ROWS>(a, xs, bar, tile * ROWS);
     unsigned phase = 0;
 
     for (; tile < ntiles; tile += gridDim.x) {
@@ -219,7 +229,7 @@ __global__ void __launch_bounds__(NT, 2) dsp_tuned_kernel(const __grid_constant_
         // ------------------------------ FIR ------------------------------
         // lanes alternate rows; a thread owns outputs t = 8j .. 8j+7 of its row
         for (int th = tid; th < ROWS * 256; th += NT) {
-            const int r = th & 1, j = th >> 1;
+            const int r = ROWS == 1 ? 0 : (th % ROWS), j = ROWS == 1 ? th : (th / ROWS);
             const float4* src = reinterpret_cast<const float4*>(xs + r * XS_PITCH) + 2 * j;
             float acc[8];
 #pragma unroll
@@ -259,19 +269,19 @@ __global__ void __launch_bounds__(NT, 2) dsp_tuned_kernel(const __grid_constant_
         }
         __syncthreads();
         // xs is free again: fetch the next tile while the STFT runs
-        if (tid == 0 && tile + gridDim.x < ntiles) issue_tile_loads(a, xs, bar, (tile + gridDim.x) * ROWS);
+        if (tid == 0 && tile + gridDim.x < ntiles) issue_tile_loads<ROWS>(a, xs, bar, (tile + gridDim.x) * ROWS);
 
         // ------------------------------ STFT ------------------------------
         // rows sit in Ls with the same 16-byte phase as their global address
         float* myscr = scr + (tid >> 3) * 256;
 #pragma unroll 1
-        for (int round = 0; round < 3; ++round) {
-            const int task = warp + NWARPS * round;          // 0..17
-            if (task >= NTASKS) break;                       // warp-uniform
-            // tasks 0..15: row = task / 8, frames (task % 8) + 8 q;  task 16: frame 32 of row q
-            const bool full = task < 16;
+        for (int round = 0; round < C::ROUNDS; ++round) {
+            const int task = warp + NWARPS * round;
+            if (task >= C::NTASKS) break;                    // warp-uniform
+            // tasks 0..8*ROWS-1: row = task / 8, frames (task % 8) + 8 q;  last task: frame 32 of row q
+            const bool full = task < 8 * ROWS;
             const bool valid = full || q < ROWS;
-            const int r = full ? (task >> 3) : (q & (ROWS - 1));
+            const int r = full ? (task >> 3) : (q % ROWS);
             const int m = full ? (task & 7) + 8 * q : 32;
             const float* yseg = ys + r * YS_PITCH + m * 64;  // extended position 64 m
 
@@ -360,37 +370,32 @@ __global__ void __launch_bounds__(NT, 2) dsp_tuned_kernel(const __grid_constant_
         }
         __syncthreads();
 
-        // ------------------------------ row statistics ------------------------------
-        if (warp < ROWS) {
-            double d1 = 0.0, d2 = 0.0;
+        // ---------------- row statistics + normalise + store ----------------
+        // Every warp reduces the 264 partials of a row itself, in the same fixed order
+        // (bit-stable, no atomics, no extra barrier): float within a lane, double across lanes.
+        const int nrows = (a.rows - row0) < ROWS ? (int)(a.rows - row0) : ROWS;
+        for (int r = 0; r < nrows; ++r) {
+            float p1 = 0.0f, p2 = 0.0f;
             for (int i = lane; i < NF * 8; i += 32) {
-                const float2 p = stat[warp * NF * 8 + i];
-                d1 += (double)p.x;
-                d2 += (double)p.y;
+                const float2 p = stat[r * NF * 8 + i];
+                p1 += p.x;
+                p2 += p.y;
             }
+            double d1 = (double)p1, d2 = (double)p2;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 d1 += __shfl_xor_sync(0xffffffffu, d1, o);
                 d2 += __shfl_xor_sync(0xffffffffu, d2, o);
             }
-            if (lane == 0) {
-                const double mean = d1 / (double)ROW_OUT;
-                double var = d2 / (double)ROW_OUT - mean * mean;
-                var = var > 0.0 ? var : 0.0;
-                const float inv = (float)(1.0 / (sqrt(var) + (double)a.z_eps));
-                rowstat[2 * warp] = inv;
-                rowstat[2 * warp + 1] = (float)(-mean) * inv;
-            }
-        }
-        __syncthreads();
+            const double mean = d1 * (1.0 / (double)ROW_OUT);
+            const double vard = d2 * (1.0 / (double)ROW_OUT) - mean * mean;
+            const float var = vard > 0.0 ? (float)vard : 0.0f;
+            const float inv = 1.0f / (sqrtf(var) + a.z_eps);
+            const float c = -(float)mean * inv;
 
-        // ------------------------------ normalise + store ------------------------------
-        const int nrows = (a.rows - row0) < ROWS ? (int)(a.rows - row0) : ROWS;
-        for (int r = 0; r < nrows; ++r) {
             const int ph = (int)((row0 + r) & 3);            // float phase of the global row start
             const float* src = Ls + r * LS_PITCH + ph;
             float* dst = a.out + (row0 + r) * (long long)ROW_OUT;
-            const float inv = rowstat[2 * r], c = rowstat[2 * r + 1];
             const int head = (4 - ph) & 3;
             const int n4 = (ROW_OUT - head) >> 2;
             const int tail = ROW_OUT - head - 4 * n4;
@@ -404,8 +409,8 @@ __global__ void __launch_bounds__(NT, 2) dsp_tuned_kernel(const __grid_constant_
             if (tid < head) __stcs(dst + tid, fmaf(src[tid], inv, c));
             if (tid < tail) __stcs(dst + head + 4 * n4 + tid, fmaf(src[head + 4 * n4 + tid], inv, c));
         }
-        // The post-FIR barrier of the next iteration orders these reads of Ls / rowstat against
-        // the next tile's STFT writes.
+        // The post-FIR barrier of the next iteration orders these reads of Ls / stat against the
+        // next tile's STFT writes.
     }
 }
 
@@ -444,6 +449,19 @@ bool dsp_tuned_supported(const eegx_dsp_plan* p) {
 int dsp_tuned_table_floats() { return 8 * LANE_TABLE; }
 void dsp_tuned_fill_tables(float* host) { fill_lane_tables(host); }
 
+template <int ROWS, int NT>
+int launch_variant(const TunedArgs& a, cudaStream_t st) {
+    using C = Cfg<ROWS, NT>;
+    EEGX_CUDA_CHECK(cudaFuncSetAttribute(dsp_tuned_kernel<ROWS, NT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+    const long long ntiles = (a.rows + ROWS - 1) / ROWS;
+    const long long max_ctas = (long long)C::CTAS_PER_SM * kNumSMsB200;
+    const int grid = (int)(ntiles < max_ctas ? ntiles : max_ctas);
+    dsp_tuned_kernel<ROWS, NT><<<grid, NT, C::SMEM_BYTES, st>>>(a);
+    EEGX_CUDA_CHECK(cudaGetLastError());
+    return EEGX_OK;
+}
+
 int launch_dsp_tuned(const eegx_dsp_plan* plan, const DspArgs& d, cudaStream_t st) {
     EEGX_REQUIRE(d.onsets == nullptr, EEGX_ERR_ARG, "tuned kernel takes pre-cut trials only");
     EEGX_REQUIRE(plan->d_lane_tables != nullptr, EEGX_ERR_ARG, "plan has no tuned tables");
@@ -455,14 +473,11 @@ int launch_dsp_tuned(const eegx_dsp_plan* plan, const DspArgs& d, cudaStream_t s
     a.log_eps4 = 4.0f * plan->log_eps;
     a.z_eps = plan->z_eps;
     for (int i = 0; i < 65; ++i) a.taps_rev[i] = plan->h_taps[64 - i];
-    EEGX_CUDA_CHECK(cudaFuncSetAttribute(dsp_tuned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)SMEM_BYTES));
-    const long long ntiles = (d.rows + ROWS - 1) / ROWS;
-    const long long max_ctas = 2LL * kNumSMsB200;
-    const int grid = (int)(ntiles < max_ctas ? ntiles : max_ctas);
-    dsp_tuned_kernel<<<grid, NT, SMEM_BYTES, st>>>(a);
-    EEGX_CUDA_CHECK(cudaGetLastError());
-    return EEGX_OK;
+    switch (plan->tuned_variant) {
+        case 1: return launch_variant<1, 96>(a, st);    // 4 CTAs/SM x 3 warps, 1 row per tile
+        case 2: return launch_variant<2, 192>(a, st);   // 2 CTAs/SM x 6 warps, 2 rows per tile
+        default: return launch_variant<1, 96>(a, st);
+    }
 }
 
 }  // namespace eegx
