@@ -41,6 +41,20 @@ SIGNATURES = {
 }
 
 
+class GemmDesc(C.Structure):
+    """Mirror of eegx_gemm_desc (include/eegx.h)."""
+    _fields_ = [("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64), ("batch", C.c_int64),
+                ("lda", C.c_int64), ("ldb", C.c_int64), ("ldd", C.c_int64),
+                ("stride_a", C.c_int64), ("stride_b", C.c_int64), ("stride_d", C.c_int64),
+                ("a_mn_major", C.c_int32), ("b_mn_major", C.c_int32), ("out_f32", C.c_int32),
+                ("epilogue", C.c_int32), ("accumulate", C.c_int32), ("force_block_n", C.c_int32),
+                ("alpha", C.c_float), ("reserved", C.c_int32)]
+
+
+SIGNATURES["eegx_gemm_bf16"] = (C.c_int, [C.POINTER(GemmDesc), C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p])
+
+
 class EegxError(RuntimeError):
     """A libeegx entry point returned a negative status."""
 

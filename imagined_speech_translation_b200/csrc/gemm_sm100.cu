@@ -1,0 +1,455 @@
+// bf16 GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM, operands
+// staged by TMA) -- the contraction core of the encoder ("library-call
+// sites that become sm_100a kernels": conv-as-GEMM, Linear, attention/FFN projections).
+//
+//   D[b] (M x N) = A[b] (M x K) * B[b] (N x K)^T  (+ bias[N]) (+ erf-GELU) (+ D[b] when accumulating)
+//
+// A and B are bf16, each either K-major (K contiguous; "row-major" M x K / N x K) or MN-major
+// (stored K x M / K x N), selected per operand -- so the forward (x W^T), the data gradient
+// (dy W) and the weight gradient (dy^T x) of a Linear layer all run on this one kernel without
+// transposing anything in HBM.  D is bf16 or fp32, row-major.  fp32 accumulation.
+//
+// Structure (persistent, warp-specialised; one CTA per SM, 192 threads):
+//   warp 0     TMA producer: cp.async.bulk.tensor (128B swizzle) into a STAGES-deep smem ring,
+//              completion on "full" mbarriers.
+//   warp 1     MMA issuer: one elected lane issues tcgen05.mma (128 x BLOCK_N x 16 per
+//              instruction); tcgen05.commit releases smem slots ("empty") and publishes the
+//              accumulator ("tmem_full").  Two accumulator stages in TMEM so the epilogue of
+//              tile i overlaps the main loop of tile i+1.
+//   warps 2-5  epilogue: tcgen05.ld (TMEM -> registers), bias / GELU / accumulate, convert,
+//              128-bit global stores; then hand the TMEM stage back ("tmem_empty").
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "eegx_common.h"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;          // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 4;
+constexpr unsigned WATCHDOG_SPINS = 1u << 27;
+
+struct GemmParams {
+    long long M, N, K, batch;
+    long long ldd, stride_d;
+    const float* bias;
+    void* D;
+    int out_f32;
+    int epilogue;      // 0 none, 1 bias, 2 bias + gelu
+    int accumulate;    // D += result (fp32 or bf16 read-modify-write)
+    float alpha;
+};
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Spin with a watchdog: a protocol bug traps (kernel error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > WATCHDOG_SPINS) asm volatile("trap;");
+    }
+}
+
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, unsigned bar, int c0,
+                                            int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(unsigned smem_dst, unsigned ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(unsigned taddr, unsigned ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
+                                          unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Arrive on an mbarrier once all previously issued tcgen05.mma have completed.
+__device__ __forceinline__ void umma_commit(unsigned bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
+    unsigned r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor, version 1).
+//   K-major : rows of 128 B (64 bf16 along K), 8-row atoms of 1024 B stacked along M/N -> SBO = 1024 B.
+//   MN-major: rows of 128 B (64 bf16 along M/N), one row per k; 8-k atoms of 1024 B stacked along K
+//             -> SBO = 1024 B; the next 64-wide M/N block is a separate TMA box -> LBO = box bytes.
+__device__ __forceinline__ unsigned long long make_smem_desc(unsigned saddr, unsigned lbo_bytes, unsigned sbo_bytes) {
+    unsigned long long d = 0;
+    d |= (unsigned long long)((saddr >> 4) & 0x3FFF);
+    d |= (unsigned long long)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (unsigned long long)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= 1ull << 46;   // descriptor version (Blackwell)
+    d |= 2ull << 61;   // SWIZZLE_128B
+    return d;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+template <int BLOCK_N, int STAGES>
+struct SmemLayout {
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+    static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int NUM_BARS = 2 * STAGES + 4;
+    static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;  // + tmem ptr + alignment slack
+};
+
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const GemmParams p) {
+    using L = SmemLayout<BLOCK_N, STAGES>;
+    extern __shared__ unsigned char smem_raw[];
+    // 1024-byte alignment required by the 128B swizzle atoms
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const unsigned smem_base = smem_u32(smem);
+    const unsigned bar_base = smem_base + L::BAR_OFFSET;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tmem_full_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+    auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+    unsigned* tmem_ptr_smem = reinterpret_cast<unsigned*>(smem + L::BAR_OFFSET + L::NUM_BARS * 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr unsigned TMEM_COLS = 2 * BLOCK_N;   // two accumulator stages (power of two >= 32)
+
+    const long long m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
+    const long long n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
+    const long long tiles_per_batch = m_blocks * n_blocks;
+    const long long num_tiles = tiles_per_batch * p.batch;
+    const int num_kb = (int)((p.K + BLOCK_K - 1) / BLOCK_K);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<unsigned long long>(&map_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<unsigned long long>(&map_b)) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tmem_full_bar(s), 1);
+            mbar_init(tmem_empty_bar(s), NUM_EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            unsigned phase = 0;
+            for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const long long bi = tile / tiles_per_batch;
+                const long long rem = tile - bi * tiles_per_batch;
+                const int n_blk = (int)(rem / m_blocks), m_blk = (int)(rem % m_blocks);   // m fastest: B tile stays hot in L2
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const unsigned a_dst = smem_base + stage * L::STAGE_BYTES;
+                    const unsigned b_dst = a_dst + L::A_BYTES;
+                    mbar_expect_tx(full_bar(stage), L::STAGE_BYTES);
+                    if (!A_MN) {
+                        tma_load_3d(a_dst, &map_a, full_bar(stage), kb * BLOCK_K, m_blk * BLOCK_M, (int)bi);
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < BLOCK_M / 64; ++h)
+                            tma_load_3d(a_dst + h * (64 * BLOCK_K * 2), &map_a, full_bar(stage),
+                                        m_blk * BLOCK_M + h * 64, kb * BLOCK_K, (int)bi);
+                    }
+                    if (!B_MN) {
+                        tma_load_3d(b_dst, &map_b, full_bar(stage), kb * BLOCK_K, n_blk * BLOCK_N, (int)bi);
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < BLOCK_N / 64; ++h)
+                            tma_load_3d(b_dst + h * (64 * BLOCK_K * 2), &map_b, full_bar(stage),
+                                        n_blk * BLOCK_N + h * 64, kb * BLOCK_K, (int)bi);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            // instruction descriptor: D = F32, A = B = BF16, majors, N >> 3, M >> 4
+            const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                                   ((B_MN ? 1u : 0u) << 16) | ((unsigned)(BLOCK_N >> 3) << 17) |
+                                   ((unsigned)(BLOCK_M >> 4) << 24);
+            int stage = 0;
+            unsigned phase = 0;
+            int acc = 0;
+            unsigned acc_phase = 0;
+            for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);
+                tc_fence_after();
+                const unsigned tmem_d = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const unsigned a_addr = smem_base + stage * L::STAGE_BYTES;
+                    const unsigned b_addr = a_addr + L::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        // K-major: +32 bytes per 16 elements inside the swizzle row.
+                        // MN-major: +2 k-atoms of 1024 bytes.
+                        const unsigned long long adesc =
+                            A_MN ? make_smem_desc(a_addr + k * 2048, 64 * BLOCK_K * 2, 1024)
+                                 : make_smem_desc(a_addr + k * 32, 16, 1024);
+                        const unsigned long long bdesc =
+                            B_MN ? make_smem_desc(b_addr + k * 2048, 64 * BLOCK_K * 2, 1024)
+                                 : make_smem_desc(b_addr + k * 32, 16, 1024);
+                        umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(stage));          // frees the smem slot when the MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tmem_full_bar(acc));            // accumulator complete
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
+        int acc = 0;
+        unsigned acc_phase = 0;
+        for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const long long bi = tile / tiles_per_batch;
+            const long long rem = tile - bi * tiles_per_batch;
+            const int n_blk = (int)(rem / m_blocks), m_blk = (int)(rem % m_blocks);
+            mbar_wait(tmem_full_bar(acc), acc_phase);
+            tc_fence_after();
+            const long long row = (long long)m_blk * BLOCK_M + quarter * 32 + lane;
+            const bool row_ok = row < p.M;
+            const unsigned taddr = tmem_base + acc * BLOCK_N + ((unsigned)(quarter * 32) << 16);
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                float v[32];
+                tmem_ld32(taddr + c * 32, v);
+                const long long col0 = (long long)n_blk * BLOCK_N + c * 32;
+                if (row_ok && col0 < p.N) {
+                    const bool full = col0 + 32 <= p.N;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
+                    if (p.epilogue >= 1) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (full || col0 + i < p.N) v[i] += __ldg(p.bias + col0 + i);
+                    }
+                    if (p.epilogue == 2) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+                    }
+                    const long long off = bi * p.stride_d + row * p.ldd + col0;
+                    if (p.out_f32) {
+                        float* d = reinterpret_cast<float*>(p.D) + off;
+                        if (full && (p.ldd & 3) == 0) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                                if (p.accumulate) {
+                                    const float4 old = *reinterpret_cast<const float4*>(d + i);
+                                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                                }
+                                *reinterpret_cast<float4*>(d + i) = o;
+                            }
+                        } else {
+                            for (int i = 0; i < 32; ++i)
+                                if (col0 + i < p.N) d[i] = p.accumulate ? d[i] + v[i] : v[i];
+                        }
+                    } else {
+                        __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + off;
+                        if (full && (p.ldd & 7) == 0 && !p.accumulate) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 8) {
+                                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i], v[i + 1]);
+                                __nv_bfloat162 h1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
+                                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]);
+                                __nv_bfloat162 h3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
+                                uint4 o;
+                                o.x = *reinterpret_cast<unsigned*>(&h0); o.y = *reinterpret_cast<unsigned*>(&h1);
+                                o.z = *reinterpret_cast<unsigned*>(&h2); o.w = *reinterpret_cast<unsigned*>(&h3);
+                                *reinterpret_cast<uint4*>(d + i) = o;
+                            }
+                        } else {
+                            for (int i = 0; i < 32; ++i)
+                                if (col0 + i < p.N)
+                                    d[i] = __float2bfloat16(p.accumulate ? __bfloat162float(d[i]) + v[i] : v[i]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// 3-D bf16 tensor map: dims (inner, rows, batch); box (box_inner, box_rows, 1); 128B swizzle.
+int make_map(CUtensorMap* map, const void* base, long long inner, long long rows, long long batch,
+             long long ld_elems, long long batch_stride_elems, int box_inner, int box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    EEGX_REQUIRE(enc != nullptr, EEGX_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)ld_elems * 2, (cuuint64_t)(batch > 1 ? batch_stride_elems : ld_elems * rows) * 2};
+    cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    EEGX_REQUIRE(r == CUDA_SUCCESS, EEGX_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d "
+                 "(inner=%lld rows=%lld batch=%lld ld=%lld)", (int)r, inner, rows, batch, ld_elems);
+    return EEGX_OK;
+}
+
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int grid, cudaStream_t st) {
+    using L = SmemLayout<BLOCK_N, STAGES>;
+    auto kern = gemm_bf16_kernel<BLOCK_N, STAGES, A_MN, B_MN>;
+    EEGX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(ma, mb, p);
+    EEGX_CUDA_CHECK(cudaGetLastError());
+    return EEGX_OK;
+}
+
+template <int BLOCK_N, int STAGES>
+int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p,
+                   int grid, cudaStream_t st) {
+    if (!a_mn && !b_mn) return launch<BLOCK_N, STAGES, false, false>(ma, mb, p, grid, st);
+    if (!a_mn && b_mn) return launch<BLOCK_N, STAGES, false, true>(ma, mb, p, grid, st);
+    if (a_mn && !b_mn) return launch<BLOCK_N, STAGES, true, false>(ma, mb, p, grid, st);
+    return launch<BLOCK_N, STAGES, true, true>(ma, mb, p, grid, st);
+}
+
+}  // namespace
+
+extern "C" int eegx_gemm_bf16(const eegx_gemm_desc* d, const void* A, const void* B, const float* bias,
+                              void* D, void* stream) {
+    if (int rc = eegx::require_sm100()) return rc;
+    EEGX_REQUIRE(d && A && B && D, EEGX_ERR_ARG, "desc/A/B/D must not be NULL");
+    EEGX_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0 && d->batch > 0, EEGX_ERR_SHAPE,
+                 "bad sizes M=%lld N=%lld K=%lld batch=%lld", (long long)d->M, (long long)d->N,
+                 (long long)d->K, (long long)d->batch);
+    EEGX_REQUIRE(d->epilogue >= 0 && d->epilogue <= 2, EEGX_ERR_ARG, "bad epilogue %d", d->epilogue);
+    EEGX_REQUIRE(d->epilogue == 0 || bias != nullptr, EEGX_ERR_ARG, "epilogue %d needs a bias", d->epilogue);
+    EEGX_REQUIRE(eegx::aligned16(A) && eegx::aligned16(B) && eegx::aligned16(D), EEGX_ERR_ALIGN,
+                 "A, B, D must be 16-byte aligned");
+    EEGX_REQUIRE((d->lda % 8) == 0 && (d->ldb % 8) == 0 && (d->stride_a % 8) == 0 && (d->stride_b % 8) == 0,
+                 EEGX_ERR_ALIGN, "lda/ldb/batch strides must be multiples of 8 elements (TMA: 16 bytes)");
+    const long long a_inner = d->a_mn_major ? d->M : d->K, a_rows = d->a_mn_major ? d->K : d->M;
+    const long long b_inner = d->b_mn_major ? d->N : d->K, b_rows = d->b_mn_major ? d->K : d->N;
+    EEGX_REQUIRE(d->lda >= a_inner && d->ldb >= b_inner && d->ldd >= d->N, EEGX_ERR_SHAPE,
+                 "leading dimensions smaller than the contiguous extent");
+
+    // tile width: the widest N tile that does not waste more than it saves
+    int block_n = 128;
+    if (d->N <= 64) block_n = 64;
+    else if (d->N > 128 && (d->N % 256 == 0 || d->N >= 1024)) block_n = 256;
+    if (d->force_block_n == 64 || d->force_block_n == 128 || d->force_block_n == 256) block_n = d->force_block_n;
+
+    CUtensorMap ma, mb;
+    int rc;
+    if (!d->a_mn_major) rc = make_map(&ma, A, d->K, d->M, d->batch, d->lda, d->stride_a, BLOCK_K, BLOCK_M);
+    else rc = make_map(&ma, A, d->M, d->K, d->batch, d->lda, d->stride_a, 64, BLOCK_K);
+    if (rc) return rc;
+    if (!d->b_mn_major) rc = make_map(&mb, B, d->K, d->N, d->batch, d->ldb, d->stride_b, BLOCK_K, block_n);
+    else rc = make_map(&mb, B, d->N, d->K, d->batch, d->ldb, d->stride_b, 64, BLOCK_K);
+    if (rc) return rc;
+
+    GemmParams p;
+    p.M = d->M; p.N = d->N; p.K = d->K; p.batch = d->batch;
+    p.ldd = d->ldd; p.stride_d = d->stride_d;
+    p.bias = bias; p.D = D;
+    p.out_f32 = d->out_f32; p.epilogue = d->epilogue; p.accumulate = d->accumulate;
+    p.alpha = d->alpha;
+
+    const long long m_blocks = (d->M + BLOCK_M - 1) / BLOCK_M;
+    const long long n_blocks = (d->N + block_n - 1) / block_n;
+    const long long tiles = m_blocks * n_blocks * d->batch;
+    const int grid = (int)(tiles < eegx::kNumSMsB200 ? tiles : eegx::kNumSMsB200);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool am = d->a_mn_major != 0, bm = d->b_mn_major != 0;
+    switch (block_n) {
+        case 64: return dispatch_major<64, 8>(am, bm, ma, mb, p, grid, st);
+        case 128: return dispatch_major<128, 6>(am, bm, ma, mb, p, grid, st);
+        default: return dispatch_major<256, 4>(am, bm, ma, mb, p, grid, st);
+    }
+}

@@ -1,0 +1,71 @@
+"""Thin Python entry points over the C ABI for the encoder's dense contractions."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+EPI_NONE, EPI_BIAS, EPI_BIAS_GELU = 0, 1, 2
+
+
+def _check_bf16(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise _lib.EegxError(f"{name} must be a CUDA tensor (no CPU fallback)")
+    if t.dtype != torch.bfloat16:
+        raise ValueError(f"{name} must be bfloat16, got {t.dtype}")
+    if t.stride(-1) != 1:
+        raise ValueError(f"{name} must have a unit innermost stride")
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
+         a_mn_major: bool = False, b_mn_major: bool = False, out: Optional[torch.Tensor] = None,
+         out_dtype: torch.dtype = torch.bfloat16, gelu: bool = False, accumulate: bool = False,
+         alpha: float = 1.0, force_block_n: int = 0) -> torch.Tensor:
+    """D = alpha * A @ B^T (+ bias) (+ GELU) (+ D) on tcgen05 tensor cores.
+
+    a: (M, K) [or (K, M) if a_mn_major], b: (N, K) [or (K, N) if b_mn_major]; optionally a
+    leading batch dim on both.  bf16 in, fp32 accumulate, bf16 or fp32 out (row-major (.., M, N)).
+    """
+    _check_bf16(a, "a")
+    _check_bf16(b, "b")
+    batched = a.dim() == 3
+    if a.dim() != b.dim() or a.dim() not in (2, 3):
+        raise ValueError("a and b must both be 2-D or both 3-D")
+    batch = a.shape[0] if batched else 1
+    if batched and b.shape[0] != batch:
+        raise ValueError("batch sizes differ")
+    ar, ac = a.shape[-2], a.shape[-1]
+    br, bc = b.shape[-2], b.shape[-1]
+    M, K = (ac, ar) if a_mn_major else (ar, ac)
+    N, Kb = (bc, br) if b_mn_major else (br, bc)
+    if K != Kb:
+        raise ValueError(f"contraction sizes differ: {K} vs {Kb}")
+    if out is None:
+        shape = (batch, M, N) if batched else (M, N)
+        out = torch.empty(shape, dtype=out_dtype, device=a.device)
+    else:
+        if out.dtype not in (torch.bfloat16, torch.float32) or out.stride(-1) != 1:
+            raise ValueError("out must be bf16 or fp32 with unit innermost stride")
+        out_dtype = out.dtype
+    d = _lib.GemmDesc()
+    d.M, d.N, d.K, d.batch = M, N, K, batch
+    d.lda, d.ldb, d.ldd = a.stride(-2), b.stride(-2), out.stride(-2)
+    d.stride_a = a.stride(0) if batched else 0
+    d.stride_b = b.stride(0) if batched else 0
+    d.stride_d = out.stride(0) if batched else 0
+    d.a_mn_major, d.b_mn_major = int(a_mn_major), int(b_mn_major)
+    d.out_f32 = int(out_dtype == torch.float32)
+    d.epilogue = EPI_NONE if bias is None else (EPI_BIAS_GELU if gelu else EPI_BIAS)
+    if gelu and bias is None:
+        raise ValueError("gelu epilogue needs a bias (pass zeros)")
+    if bias is not None and (bias.dtype != torch.float32 or not bias.is_contiguous() or bias.numel() != N):
+        raise ValueError("bias must be a contiguous fp32 vector of length N")
+    d.accumulate = int(accumulate)
+    d.force_block_n = int(force_block_n)
+    d.alpha = float(alpha)
+    _lib.check(_lib.lib().eegx_gemm_bf16(C.byref(d), _lib.ptr(a), _lib.ptr(b), _lib.ptr(bias),
+                                         _lib.ptr(out), _lib.stream_ptr()), "eegx_gemm_bf16")
+    return out

@@ -105,6 +105,41 @@ int eegx_dsp_plan_force_generic(eegx_dsp_plan* plan, int on);
 int eegx_dsp_forward(const eegx_dsp_plan* plan, const float* x, const int64_t* onsets,
                      int64_t rec_len, float* out, int64_t B, void* stream);
 
+/* ------------------------------------------------------------------------
+ * bf16 tensor-core GEMM (tcgen05 / TMEM / TMA), the contraction core of the
+ * encoder.  Replaces the cuDNN / cuBLAS library calls behind nn.Conv1d and
+ * nn.Linear in Conv1DWithAttention / BrainRegionEncoder
+ * (main_model/src/models/layers.py:30-127, brain_encoder.py:31-92; SURVEY.md
+ * section 2 "library-call sites that become sm_100a kernels").
+ *
+ *   D[b] (M x N) = alpha * A[b] (M x K) * B[b] (N x K)^T  (+ bias[N]) (+ GELU) (+ D[b])
+ *
+ * A, B: bf16.  a_mn_major = 0: A is stored M x K (K contiguous, leading dim lda);
+ *              a_mn_major = 1: A is stored K x M (M contiguous).  Same for B / N.
+ * With x (M x K), W (N x K), dy (M x N) this gives, without any transpose in HBM:
+ *   forward  y  = x W^T      : A = x  (K-major),  B = W  (K-major)
+ *   dgrad    dx = dy W       : A = dy (K-major),  B = W  (MN-major, "K" = N)
+ *   wgrad    dW = dy^T x     : A = dy (MN-major), B = x  (MN-major, "K" = M)
+ * D: bf16 (out_f32 = 0) or fp32 (out_f32 = 1), row-major, leading dim ldd.
+ * epilogue: 0 none, 1 + bias, 2 + bias then exact (erf) GELU.  accumulate: D += result.
+ * lda / ldb / batch strides: multiples of 8 elements; A, B, D 16-byte aligned.
+ * ------------------------------------------------------------------------ */
+typedef struct eegx_gemm_desc {
+    int64_t M, N, K, batch;
+    int64_t lda, ldb, ldd;
+    int64_t stride_a, stride_b, stride_d; /* batch strides in elements */
+    int32_t a_mn_major, b_mn_major;
+    int32_t out_f32;
+    int32_t epilogue;
+    int32_t accumulate;
+    int32_t force_block_n; /* 0 = auto; 64 / 128 / 256 pins the N tile (tests, tuning) */
+    float alpha;
+    int32_t reserved;
+} eegx_gemm_desc;
+
+int eegx_gemm_bf16(const eegx_gemm_desc* desc, const void* A, const void* B, const float* bias,
+                   void* D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
