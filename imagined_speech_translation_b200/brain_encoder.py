@@ -1,0 +1,122 @@
+"""Multi-region EEG encoder on the B200 path.
+
+Drop-in for the reference ``BrainRegionEncoder`` (``main_model/src/models/brain_encoder.py:11-193``):
+same constructor, parameter names / shapes and forward semantics; the four region encoders are
+``layers.Conv1DWithAttention`` and every Linear / Conv1d contraction of the fusion stage runs on
+the tcgen05 GEMM.  ``forward(list[4] of (B, C_r, T) CUDA tensors) -> (B, hidden_dim)`` float32.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import nn_ops
+from .layers import Conv1DWithAttention, _layer_norm, _mha, run_sequential
+from .nn_ops import PAD
+
+REGION_NAMES = ['frontal', 'temporal', 'central', 'parietal']
+
+
+class BrainRegionEncoder(nn.Module):
+    def __init__(self, n_timepoints, region_channel_counts, hidden_dim=768,
+                 disable_cross_region_attn=False, uniform_region_weight=False, cnn_only=False):
+        super().__init__()
+        self.region_names = list(REGION_NAMES)
+        self.region_channel_counts = region_channel_counts
+        self.disable_cross_region_attn = disable_cross_region_attn
+        self.uniform_region_weight = uniform_region_weight
+        self.n_regions = len(self.region_names)
+        self.hidden_dim = hidden_dim
+        d = hidden_dim
+
+        self.region_embeddings = nn.Embedding(self.n_regions, d)
+        nn.init.normal_(self.region_embeddings.weight, std=0.02)
+        self.temporal_scales = nn.ModuleList(
+            [nn.Conv1d(d, d, kernel_size=k, padding=k // 2) for k in (3, 7, 15, 31)])
+        self.diversity_projection = nn.Sequential(
+            nn.Linear(d * 4, d * 2), nn.GELU(), nn.Dropout(0.1), nn.Linear(d * 2, d), nn.LayerNorm(d))
+        if not uniform_region_weight:
+            self.region_importance = nn.Parameter(torch.randn(self.n_regions) * 0.5)
+            self.region_gate = nn.Sequential(
+                nn.Linear(d, d // 2), nn.GELU(), nn.Dropout(0.1), nn.Linear(d // 2, self.n_regions), nn.Sigmoid())
+        self.region_encoders = nn.ModuleDict({
+            name: Conv1DWithAttention(region_channel_counts[name], n_timepoints, d, cnn_only=cnn_only)
+            for name in self.region_names})
+        if not disable_cross_region_attn:
+            layer = nn.TransformerEncoderLayer(d_model=d, nhead=12, dim_feedforward=d * 4, dropout=0.1,
+                                               activation='gelu', batch_first=True, norm_first=True)
+            self.fusion_transformer = nn.TransformerEncoder(layer, num_layers=2, enable_nested_tensor=False)
+            self.cross_region_attention = nn.MultiheadAttention(embed_dim=d, num_heads=8, dropout=0.1,
+                                                                batch_first=True)
+        self.feature_enhancer = nn.Sequential(
+            nn.Linear(d, d * 2), nn.GELU(), nn.Dropout(0.1), nn.Linear(d * 2, d), nn.LayerNorm(d))
+
+    # -- brain_encoder.py:94-113: four Conv1d over the length-4 region axis, GELU, mean, project
+    def apply_multi_scale_processing(self, x):
+        B, R, d = x.shape                                       # (B, 4, d) bf16, channels-last already
+        M = B * (R + 2 * PAD)
+        buf = nn_ops.guard_pad(x)
+        valid = torch.zeros(R + 2 * PAD, device=x.device)
+        valid[PAD:PAD + R] = 1.0
+        feats = []
+        for conv in self.temporal_scales:
+            k = conv.kernel_size[0]
+            w = conv.weight
+            if k > 2 * R - 1:       # only offsets -(R-1)..(R-1) can ever meet data: drop the dead taps
+                c = k // 2
+                w = w[:, :, c - (R - 1): c + R]
+            y = nn_ops.conv1d_cl(buf, w, conv.bias, M).float().view(B, R + 2 * PAD, d)
+            y = F.gelu(y) * valid.view(1, -1, 1)
+            feats.append(y.sum(dim=1) / R)
+        ms = torch.stack(feats, dim=1).reshape(B, 4 * d).to(torch.bfloat16)
+        ms = run_sequential(self.diversity_projection, ms)
+        return ms.unsqueeze(1).expand(-1, R, -1)
+
+    def compute_dynamic_region_weights(self, x):
+        pooled = x.float().mean(dim=1).to(torch.bfloat16)
+        dyn = run_sequential(self.region_gate, pooled).float()
+        if hasattr(self, 'region_importance'):
+            static = F.softmax(self.region_importance, dim=0)
+            return F.softmax(0.7 * static.unsqueeze(0) + 0.3 * dyn, dim=1)
+        return F.softmax(dyn, dim=1)
+
+    def _fusion_layer(self, layer: nn.TransformerEncoderLayer, x):
+        # norm_first: x + drop(MHA(LN1 x)); x + drop(W2 drop(gelu(W1 LN2 x)))
+        a = _mha(layer.self_attn, _layer_norm(x, layer.norm1), None, True)
+        x = (x.float() + layer.dropout1(a.float())).to(torch.bfloat16)
+        h = nn_ops.linear(_layer_norm(x, layer.norm2), layer.linear1.weight, layer.linear1.bias)
+        h = layer.dropout(F.gelu(h.float())).to(torch.bfloat16)
+        h = nn_ops.linear(h, layer.linear2.weight, layer.linear2.bias)
+        return (x.float() + layer.dropout2(h.float())).to(torch.bfloat16)
+
+    def forward(self, eeg_data):
+        feats = [self.region_encoders[name](eeg_data[i]) for i, name in enumerate(self.region_names)]
+        x = torch.stack(feats, dim=1)                            # (B, 4, d) fp32
+        ms = self.apply_multi_scale_processing(x.to(torch.bfloat16))
+        x = x + 0.3 * ms.float()
+        x = x + 0.4 * self.region_embeddings.weight.unsqueeze(0)
+        if not self.disable_cross_region_attn:
+            xt = x.to(torch.bfloat16)
+            for layer in self.fusion_transformer.layers:
+                xt = self._fusion_layer(layer, xt)
+            xc = _mha(self.cross_region_attention, xt, None, True)
+            gate = torch.sigmoid(run_sequential(self.feature_enhancer,
+                                                xt.float().mean(dim=1).to(torch.bfloat16)).float()).unsqueeze(1)
+            x = xt.float() + gate * xc.float()
+        if self.uniform_region_weight or not hasattr(self, 'region_importance'):
+            fused = x.mean(dim=1)
+        else:
+            w = self.compute_dynamic_region_weights(x)
+            fused = (x * w.unsqueeze(-1)).sum(dim=1)
+        enhanced = run_sequential(self.feature_enhancer, fused.to(torch.bfloat16)).float()
+        return fused + 0.3 * enhanced
+
+    def get_region_weights(self):
+        """Same report as the reference (brain_encoder.py:195-214)."""
+        if hasattr(self, 'region_importance') and not self.uniform_region_weight:
+            return {'names': self.region_names,
+                    'softmax': F.softmax(self.region_importance, dim=0).data.cpu().numpy(),
+                    'has_dynamic': hasattr(self, 'region_gate')}
+        return {'names': self.region_names, 'softmax': [1.0 / self.n_regions] * self.n_regions,
+                'has_dynamic': False}

@@ -414,10 +414,11 @@ extern "C" int eegx_gemm_bf16(const eegx_gemm_desc* d, const void* A, const void
                  "A, B, D must be 16-byte aligned");
     EEGX_REQUIRE((d->lda % 8) == 0 && (d->ldb % 8) == 0 && (d->stride_a % 8) == 0 && (d->stride_b % 8) == 0,
                  EEGX_ERR_ALIGN, "lda/ldb/batch strides must be multiples of 8 elements (TMA: 16 bytes)");
-    const long long a_inner = d->a_mn_major ? d->M : d->K, a_rows = d->a_mn_major ? d->K : d->M;
-    const long long b_inner = d->b_mn_major ? d->N : d->K, b_rows = d->b_mn_major ? d->K : d->N;
-    EEGX_REQUIRE(d->lda >= a_inner && d->ldb >= b_inner && d->ldd >= d->N, EEGX_ERR_SHAPE,
-                 "leading dimensions smaller than the contiguous extent");
+    // lda / ldb may be SMALLER than the contiguous extent: rows then overlap in memory, which is
+    // how a channels-last Conv1d runs as an implicit-im2col GEMM (row r = k consecutive time steps).
+    EEGX_REQUIRE(d->lda >= 8 && d->ldb >= 8 && d->ldd >= d->N, EEGX_ERR_SHAPE,
+                 "leading dimensions too small (lda=%lld ldb=%lld ldd=%lld)", (long long)d->lda,
+                 (long long)d->ldb, (long long)d->ldd);
 
     // tile width: the widest N tile that does not waste more than it saves
     int block_n = 128;

@@ -1,0 +1,171 @@
+"""Autograd glue between torch tensors and the libeegx contractions.
+
+Every dense contraction of the encoder (nn.Linear and nn.Conv1d call sites of reference
+``main_model/src/models/layers.py`` / ``brain_encoder.py``) goes through ``ops.gemm`` -- the
+tcgen05 kernel -- in all three directions (forward, data gradient, weight gradient).
+Activations are bf16, channels-last; parameters stay fp32 "master" tensors and are packed to
+bf16 once per optimizer step (cache keyed on the parameter's version counter).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+
+PAD = 4   # largest Conv1d padding in the encoder (kernel 9, layers.py:30)
+
+_pack_cache: dict = {}
+
+
+def _cached(param: torch.Tensor, tag: str, make):
+    """bf16 pack of a parameter (or of a row-slice view of one), rebuilt when the parameter's
+    version counter moves (i.e. after an optimizer step).  The entry keeps the base tensor alive,
+    so its id() cannot be recycled while the entry exists."""
+    base = param._base if param._base is not None else param
+    key = (id(base), param.storage_offset(), tuple(param.shape), tag)
+    hit = _pack_cache.get(key)
+    ver = base._version
+    if hit is not None and hit[0] == ver and hit[2] is base:
+        return hit[1]
+    with torch.no_grad():
+        val = make(param.detach())
+    _pack_cache[key] = (ver, val, base)
+    return val
+
+
+def clear_pack_cache():
+    _pack_cache.clear()
+
+
+def _w_linear(w):            # (N, K) fp32 -> bf16, rows zero-padded to a multiple of 8 (TMA row pitch of dy)
+    def make(p):
+        n_pad = (-p.shape[0]) % 8
+        p16 = p.to(torch.bfloat16)
+        return (torch.nn.functional.pad(p16, (0, 0, 0, n_pad)) if n_pad else p16).contiguous()
+    return _cached(w, "lin", make)
+
+
+def _w_conv_fwd(w):          # (Cout, Cin, k) -> (Cout, k*Cin) bf16, K index = tap*Cin + ci
+    return _cached(w, "convf", lambda p: p.permute(0, 2, 1).reshape(p.shape[0], -1).to(torch.bfloat16).contiguous())
+
+
+def _w_conv_dgrad(w):        # (Cout, Cin, k) -> (k*Cout, Cin) bf16 with taps flipped (K x N, N contiguous)
+    return _cached(w, "convd", lambda p: p.flip(2).permute(2, 0, 1).reshape(-1, p.shape[1]).to(torch.bfloat16).contiguous())
+
+
+class _Linear(torch.autograd.Function):
+    """y = x W^T + b (optionally GELU) on (M, K) bf16 rows; dW returned in fp32 for the master weight."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gelu):
+        w16 = _w_linear(weight)
+        N, n_pad = weight.shape[0], w16.shape[0] - weight.shape[0]
+        b32 = bias.detach().float().contiguous() if bias is not None else None
+        if gelu and b32 is None:
+            b32 = torch.zeros(N, device=x.device)
+        if b32 is not None and n_pad:
+            b32 = torch.nn.functional.pad(b32, (0, n_pad))
+        if gelu:
+            pre = ops.gemm(x, w16, b32)                 # keep the pre-activation for backward
+            y = torch.nn.functional.gelu(pre.float()).to(torch.bfloat16)
+            ctx.save_for_backward(x, weight, pre)
+        else:
+            y = ops.gemm(x, w16, b32)
+            ctx.save_for_backward(x, weight, None)
+        ctx.has_bias = bias is not None
+        ctx.gelu = gelu
+        ctx.n_pad = n_pad
+        return y[:, :N] if n_pad else y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, pre = ctx.saved_tensors
+        N = weight.shape[0]
+        dy = torch.nn.functional.pad(dy, (0, ctx.n_pad)) if ctx.n_pad else dy.contiguous()
+        if ctx.gelu:
+            p = pre.float()
+            cdf = 0.5 * (1.0 + torch.erf(p * 0.7071067811865476))
+            pdf = torch.exp(-0.5 * p * p) * 0.3989422804014327
+            dy = (dy.float() * (cdf + p * pdf)).to(torch.bfloat16)
+        w16 = _w_linear(weight)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.gemm(dy, w16, b_mn_major=True)                                   # (M,N) @ (N,K)
+        if ctx.needs_input_grad[1]:
+            dw = ops.gemm(dy, x, a_mn_major=True, b_mn_major=True, out_dtype=torch.float32)[:N]   # dy^T @ x
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.float().sum(0)[:N]
+        return dx, dw, db, None
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+           gelu: bool = False) -> torch.Tensor:
+    """nn.Linear on the last dim of a bf16 tensor, through the tcgen05 GEMM."""
+    shp = x.shape
+    x2 = x.reshape(-1, shp[-1])
+    if x2.stride(-1) != 1 or (x2.stride(0) % 8) != 0:
+        x2 = x2.contiguous()
+    K = x2.shape[1]
+    if K % 8 != 0:      # TMA needs 16-byte row pitch: pad the contraction dim with zeros
+        raise ValueError(f"in_features={K} must be a multiple of 8 on this path")
+    y = _Linear.apply(x2, weight, bias, gelu)
+    return y.reshape(*shp[:-1], weight.shape[0])
+
+
+def guard_pad(x_cl: torch.Tensor) -> torch.Tensor:
+    """(B, T, C) channels-last -> guarded flat buffer ((B*(T+2*PAD) + 2*PAD), C) with zero rows
+    around every trial, so a Conv1d over time is a GEMM on overlapping rows (implicit im2col)."""
+    B, T, C = x_cl.shape
+    xp = torch.nn.functional.pad(x_cl, (0, 0, PAD, PAD))                 # per-trial zero padding
+    flat = xp.reshape(B * (T + 2 * PAD), C)
+    return torch.nn.functional.pad(flat, (0, 0, PAD, PAD))               # global guard rows
+
+
+class _ConvCL(torch.autograd.Function):
+    """Conv1d (stride 1, 'same' zero padding k//2) on a guarded channels-last buffer.
+
+    buf: ((M + 2*PAD), Cin) bf16 with M = B*(T+2*PAD); returns (M, Cout) bf16 -- rows that fall in
+    a trial's padding zone hold don't-care values and must be masked by the caller.
+    """
+
+    @staticmethod
+    def forward(ctx, buf, weight, bias, M):
+        Cout, Cin, k = weight.shape
+        p = k // 2
+        a = buf.as_strided((M, k * Cin), (Cin, 1), buf.storage_offset() + (PAD - p) * Cin)
+        b32 = bias.detach().float().contiguous() if bias is not None else None
+        y = ops.gemm(a, _w_conv_fwd(weight), b32)
+        ctx.save_for_backward(buf, weight)
+        ctx.M = M
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        buf, weight = ctx.saved_tensors
+        Cout, Cin, k = weight.shape
+        p = k // 2
+        M = ctx.M
+        dy = dy.contiguous()                              # (M, Cout); zero on padding rows
+        dbuf = dw = db = None
+        if ctx.needs_input_grad[1]:
+            a_view = buf.as_strided((M, k * Cin), (Cin, 1), buf.storage_offset() + (PAD - p) * Cin)
+            dwf = ops.gemm(dy, a_view, a_mn_major=True, b_mn_major=True, out_dtype=torch.float32)  # (Cout, k*Cin)
+            dw = dwf.view(Cout, k, Cin).permute(0, 2, 1).contiguous()
+        if ctx.needs_input_grad[0]:
+            # dx = conv of the (guarded) dy with the flipped taps: rows overlap again
+            dyg = torch.nn.functional.pad(dy, (0, 0, PAD, PAD))
+            a = dyg.as_strided((M, k * Cout), (Cout, 1), (PAD - p) * Cout)
+            dx = ops.gemm(a, _w_conv_dgrad(weight), b_mn_major=True)            # (M, Cin)
+            dbuf = torch.nn.functional.pad(dx, (0, 0, PAD, PAD))
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.float().sum(0)
+        return dbuf, dw, db, None
+
+
+def conv1d_cl(buf: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], M: int) -> torch.Tensor:
+    if weight.shape[1] % 8 != 0:
+        raise ValueError("Conv1d in_channels must be a multiple of 8 on this path")
+    return _ConvCL.apply(buf, weight, bias, M)

@@ -123,6 +123,9 @@ int eegx_dsp_forward(const eegx_dsp_plan* plan, const float* x, const int64_t* o
  * D: bf16 (out_f32 = 0) or fp32 (out_f32 = 1), row-major, leading dim ldd.
  * epilogue: 0 none, 1 + bias, 2 + bias then exact (erf) GELU.  accumulate: D += result.
  * lda / ldb / batch strides: multiples of 8 elements; A, B, D 16-byte aligned.
+ * lda (ldb) may be smaller than the contiguous extent: rows then overlap, which is how a
+ * channels-last Conv1d (kernel k, C_in channels) runs as an implicit-im2col GEMM with
+ * K = k * C_in and lda = C_in (layers.py:30-47).
  * ------------------------------------------------------------------------ */
 typedef struct eegx_gemm_desc {
     int64_t M, N, K, batch;
