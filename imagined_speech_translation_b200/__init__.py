@@ -8,3 +8,7 @@ from .preprocess import (DSP_CONFIG, DSP_CONFIG_LONG, REGION_ORDER, RegionNormal
                          SpectrogramFrontEnd, design_bandpass_fir, normalize_dense)
 
 __version__ = "0.1.0"
+from .layers import Conv1DWithAttention, FeedForwardNetwork, SqueezeExciteBlock  # noqa: F401,E402
+from .brain_encoder import BrainRegionEncoder  # noqa: F401,E402
+from .optim import FlatAdamW  # noqa: F401,E402
+from . import distributed, ops  # noqa: F401,E402

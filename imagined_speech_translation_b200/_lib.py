@@ -55,6 +55,14 @@ SIGNATURES["eegx_gemm_bf16"] = (C.c_int, [C.POINTER(GemmDesc), C.c_void_p, C.c_v
                                           C.c_void_p, C.c_void_p])
 
 
+SIGNATURES["eegx_sumsq_workspace_bytes"] = (C.c_size_t, [])
+SIGNATURES["eegx_sumsq_f32"] = (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p,
+                                          C.c_size_t, C.c_void_p])
+SIGNATURES["eegx_adamw_clip_f32"] = (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                               C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                               C.c_int64, C.c_void_p, C.c_float, C.c_float, C.c_void_p])
+
+
 class EegxError(RuntimeError):
     """A libeegx entry point returned a negative status."""
 

@@ -1,0 +1,86 @@
+"""Data-parallel plumbing: one process per GPU, trials shard by batch, one gradient all-reduce
+per optimizer step.  The reference has no distributed code; this is the
+single collective the hot path needs.  Preprocessing needs none (every stage is per trial)."""
+from __future__ import annotations
+
+import os
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def env_rank() -> Tuple[int, int, int]:
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+            int(os.environ.get("LOCAL_RANK", "0")))
+
+
+def init_from_env(backend: Optional[str] = None):
+    """torchrun-style initialisation (MASTER_ADDR / MASTER_PORT / RANK / WORLD_SIZE from the env)."""
+    rank, world, local_rank = env_rank()
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kwargs = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            kwargs["device_id"] = torch.device("cuda", local_rank)
+        dist.init_process_group(backend, **kwargs)
+    return rank, world, local_rank
+
+
+def shard_range(n_items: int, rank: int, world: int) -> range:
+    """Contiguous shard of a global batch: rank r owns [r*ceil(n/w), min(n, (r+1)*ceil(n/w)))."""
+    per = (n_items + world - 1) // world
+    return range(min(n_items, rank * per), min(n_items, (rank + 1) * per))
+
+
+def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> None:
+    """Replicas start identical: parameters AND buffers (BatchNorm running statistics) from src."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src=src, group=group)
+
+
+def allreduce_sum_(buffers: Iterable[torch.Tensor], group=None) -> None:
+    """In-place SUM all-reduce of a few large flat buffers (FlatAdamW.flat_grads())."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    for b in buffers:
+        dist.all_reduce(b, op=dist.ReduceOp.SUM, group=group)
+
+
+def allreduce_gradients(params: Sequence[torch.nn.Parameter], group=None, average: bool = True,
+                        bucket_bytes: int = 256 << 20) -> int:
+    """Bucketed gradient all-reduce for optimizers without flat buffers.  Parameters whose grad
+    is None (e.g. the BART encoder, which never runs) are skipped on every rank alike.
+    Returns the number of collectives issued."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 0
+    world = dist.get_world_size(group)
+    grads = [p.grad for p in params if p.grad is not None]
+    calls, bucket, size = 0, [], 0
+
+    def flush():
+        nonlocal calls, bucket, size
+        if not bucket:
+            return
+        flat = torch.cat([g.reshape(-1) for g in bucket])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            flat.div_(world)
+        off = 0
+        for g in bucket:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+        calls += 1
+        bucket, size = [], 0
+
+    for g in grads:
+        bucket.append(g)
+        size += g.numel() * g.element_size()
+        if size >= bucket_bytes:
+            flush()
+    flush()
+    return calls

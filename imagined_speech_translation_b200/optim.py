@@ -1,0 +1,114 @@
+"""Fused optimizer step for the train loop (flat fp32 buffers, two HBM-bound kernels per group).
+
+Mirrors what ``EEGTrainer.train_epoch`` does every ``accumulation_steps`` micro-batches
+(reference ``main_model/src/training/trainer.py:101-113``): ``clip_grad_norm_`` over *all*
+parameters, then ``AdamW.step()`` with the three learning-rate groups of
+``config/training_config.py:55-77``.  Update rule: ``torch.optim.AdamW`` (SURVEY.md section 7:
+the reference's ``transformers.AdamW`` no longer exists; parity at the optimizer is pinned
+against torch's).  Parameters that never receive a gradient (the BART *encoder*, 43.3 M
+parameters) are left untouched, exactly as torch skips ``grad is None``.
+
+Subclasses ``torch.optim.Optimizer`` so the reference's LR schedulers
+(``get_cosine_schedule_with_warmup``) drive ``param_groups[i]['lr']`` unchanged.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib, nn_ops
+
+
+class FlatAdamW(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01):
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        super().__init__(params, defaults)
+        self._flat = None          # per group: dict(p, g, m, v, params)
+        self._step = 0
+        self._norm_sq = None
+        self._ws = None
+        self.grad_scale = 1.0      # e.g. 1 / world_size when the flat grads hold an all-reduced SUM
+
+    # ------------------------------------------------------------------ flat buffers
+    def _build(self):
+        flats = []
+        for group in self.param_groups:
+            ps = [p for p in group['params'] if p.grad is not None]
+            if not ps:
+                flats.append(None)
+                continue
+            dev = ps[0].device
+            for p in ps:
+                if p.dtype != torch.float32 or not p.is_cuda:
+                    raise _lib.EegxError("FlatAdamW needs float32 CUDA parameters (no CPU fallback)")
+            sizes = [(p.numel() + 3) // 4 * 4 for p in ps]          # keep every view 16-byte aligned
+            total = sum(sizes)
+            flat_p = torch.zeros(total, device=dev)
+            flat_g = torch.zeros(total, device=dev)
+            off = 0
+            for p, n in zip(ps, sizes):
+                k = p.numel()
+                flat_p[off:off + k].copy_(p.data.reshape(-1))
+                flat_g[off:off + k].copy_(p.grad.reshape(-1))
+                p.data = flat_p[off:off + k].view_as(p)
+                p.grad = flat_g[off:off + k].view_as(p)
+                off += n
+            flats.append(dict(p=flat_p, g=flat_g, m=torch.zeros_like(flat_p), v=torch.zeros_like(flat_p),
+                              params=ps))
+        self._flat = flats
+        dev = next(f for f in flats if f is not None)['p'].device
+        self._norm_sq = torch.zeros(1, device=dev)
+        self._ws = torch.empty(_lib.lib().eegx_sumsq_workspace_bytes(), dtype=torch.uint8, device=dev)
+
+    def flat_grads(self):
+        """The flat gradient buffers (one per group that has gradients): the data-parallel
+        all-reduce runs directly on these."""
+        if self._flat is None:
+            self._build()
+        return [f['g'] for f in self._flat if f is not None]
+
+    def zero_grad(self, set_to_none: bool = False):
+        if self._flat is None:
+            return super().zero_grad(set_to_none=True)
+        for f in self._flat:
+            if f is not None:
+                f['g'].zero_()
+
+    # ------------------------------------------------------------------ step
+    @torch.no_grad()
+    def step(self, closure=None, max_grad_norm: Optional[float] = None):
+        if closure is not None:
+            raise ValueError("closure is not supported")
+        if self._flat is None:
+            self._build()
+        lib = _lib.lib()
+        st = _lib.stream_ptr()
+        self._step += 1
+        norm_ptr = None
+        if max_grad_norm is not None:
+            first = True
+            for f in self._flat:
+                if f is None:
+                    continue
+                _lib.check(lib.eegx_sumsq_f32(_lib.ptr(f['g']), f['g'].numel(), _lib.ptr(self._norm_sq),
+                                              0 if first else 1, _lib.ptr(self._ws), self._ws.numel(), st),
+                           "eegx_sumsq_f32")
+                first = False
+            norm_ptr = _lib.ptr(self._norm_sq)
+        for group, f in zip(self.param_groups, self._flat):
+            if f is None:
+                continue
+            b1, b2 = group['betas']
+            _lib.check(lib.eegx_adamw_clip_f32(
+                _lib.ptr(f['p']), _lib.ptr(f['g']), _lib.ptr(f['m']), _lib.ptr(f['v']), f['p'].numel(),
+                float(group['lr']), float(b1), float(b2), float(group['eps']), float(group['weight_decay']),
+                self._step, norm_ptr, float(max_grad_norm or 0.0), float(self.grad_scale), st),
+                "eegx_adamw_clip_f32")
+        nn_ops.clear_pack_cache()      # parameters changed behind autograd's back: repack bf16 copies
+        return None
+
+    def grad_norm(self) -> torch.Tensor:
+        """||g||_2 of the last clipped step (device scalar, no sync)."""
+        return self._norm_sq.sqrt() * self.grad_scale

@@ -1,0 +1,146 @@
+"""Training loop step on the B200 path.
+
+Mirror of the working part of the reference trainer -- ``EEGTrainer.forward_pass`` and
+``EEGTrainer.train_epoch`` (``main_model/src/training/trainer.py:40-151``) -- and of its wiring
+(``config/training_config.py:5-77``, ``scripts/train.py:199-241``): same constructor, same
+step semantics (loss / accumulation_steps, clip to grad_clip_norm, optimizer step, zero_grad,
+scheduler step, global_step; the end-of-epoch flush steps the optimizer but NOT the scheduler),
+three learning-rate groups routed by parameter-name substring.  Differences, all deliberate:
+errors are raised instead of swallowed, the loss is accumulated on the device and read back once
+per epoch instead of ``.item()`` every micro-batch, clipping + AdamW are one fused step, and under
+data parallelism the flat gradients are all-reduced once per optimizer step.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import distributed as dp
+from .optim import FlatAdamW
+
+CONFIG = {
+    # values of the reference config (training_config.py:5-52) that define the step
+    'hidden_dim': 768, 'n_timepoints': 1651, 'max_length': 16,
+    'epochs': 100, 'batch_size': 4, 'accumulation_steps': 8, 'grad_clip_norm': 1.0,
+    'brain_encoder_lr': 3e-4, 'bart_decoder_lr': 3e-5, 'projection_lr': 1e-4,
+    'warmup_steps': 500, 'weight_decay': 0.01, 'log_interval': 20, 'seed': 42,
+    # DSP front-end keys (SURVEY.md section 5 "Config / flags")
+    'fs': 256.0, 'band': (8.0, 30.0), 'numtaps': 65, 'n_fft': 256, 'hop': 64, 'log_eps': 1.0,
+}
+
+
+def get_optimizer_groups(model, config=CONFIG):
+    """Three groups by name substring, as training_config.py:55-77."""
+    enc, proj, bart = [], [], []
+    for name, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        if 'brain_encoder' in name:
+            enc.append(p)
+        elif 'eeg_to_bart' in name:
+            proj.append(p)
+        elif 'bart' in name:
+            bart.append(p)
+    return [{'params': enc, 'lr': config['brain_encoder_lr']},
+            {'params': proj, 'lr': config['projection_lr']},
+            {'params': bart, 'lr': config['bart_decoder_lr']}]
+
+
+def build_optimizer(model, config=CONFIG):
+    """scripts/train.py:210-215: AdamW(eps 1e-8, betas .9/.999, weight_decay from the config)."""
+    return FlatAdamW(get_optimizer_groups(model, config), eps=1e-8, betas=(0.9, 0.999),
+                     weight_decay=config['weight_decay'])
+
+
+def cosine_schedule_with_warmup(optimizer, num_warmup_steps, num_training_steps, num_cycles=0.5):
+    """Same multiplier as transformers.get_cosine_schedule_with_warmup (scripts/train.py:227-231);
+    note lambda(0) = 0: the first optimizer step runs with lr 0."""
+    def lr_lambda(step):
+        if step < num_warmup_steps:
+            return float(step) / float(max(1, num_warmup_steps))
+        progress = float(step - num_warmup_steps) / float(max(1, num_training_steps - num_warmup_steps))
+        return max(0.0, 0.5 * (1.0 + math.cos(math.pi * float(num_cycles) * 2.0 * progress)))
+    return torch.optim.lr_scheduler.LambdaLR(optimizer, lr_lambda)
+
+
+class EEGTrainer:
+    def __init__(self, model, tokenizer, train_loader, val_loader, optimizer, scheduler, config,
+                 front_end=None, region_channel_counts=None, process_group=None):
+        self.model = model
+        self.tokenizer = tokenizer
+        self.train_loader = train_loader
+        self.val_loader = val_loader
+        self.optimizer = optimizer
+        self.scheduler = scheduler
+        self.config = config
+        self.device = next(model.parameters()).device
+        self.front_end = front_end                      # SpectrogramFrontEnd: batch['raw'] -> regions
+        self.region_channel_counts = region_channel_counts
+        self.process_group = process_group
+        self.world_size = torch.distributed.get_world_size(process_group) \
+            if torch.distributed.is_initialized() else 1
+        self.best_bleu4 = 0.0
+        self.patience_counter = 0
+        self.global_step = 0
+        self.epoch = 0
+
+    # ------------------------------------------------------------------
+    def _regions(self, batch):
+        if 'raw' in batch and self.front_end is not None:
+            raw = batch['raw'].to(self.device, non_blocking=True)
+            return self.front_end.split_regions(self.front_end(raw), self.region_channel_counts)
+        return [r.to(self.device, non_blocking=True) for r in batch['eeg']]
+
+    def forward_pass(self, eeg, decoder_input_ids, labels):
+        feats = self.model.brain_encoder(eeg)
+        return self.model.bart_decoder(eeg_feat=feats, decoder_input_ids=decoder_input_ids, labels=labels)
+
+    def _optimizer_step(self, step_scheduler: bool):
+        clip = self.config.get('grad_clip_norm', 1.0)
+        if isinstance(self.optimizer, FlatAdamW):
+            if self.world_size > 1:
+                dp.allreduce_sum_(self.optimizer.flat_grads(), self.process_group)
+                self.optimizer.grad_scale = 1.0 / self.world_size
+            self.optimizer.step(max_grad_norm=clip)
+        else:
+            if self.world_size > 1:
+                dp.allreduce_gradients(list(self.model.parameters()), self.process_group)
+            torch.nn.utils.clip_grad_norm_(self.model.parameters(), clip)
+            self.optimizer.step()
+        self.optimizer.zero_grad()
+        if step_scheduler:
+            self.scheduler.step()
+            self.global_step += 1
+
+    def train_step(self, batch):
+        """One micro-batch: preprocess (if raw) + forward + backward of loss / accumulation_steps.
+        Returns the un-scaled loss as a device scalar (no host sync)."""
+        eeg = self._regions(batch)
+        ids = batch['decoder_input_ids'].to(self.device, non_blocking=True)
+        labels = batch['labels'].to(self.device, non_blocking=True)
+        out = self.forward_pass(eeg, ids, labels)
+        if out.loss is None:
+            raise RuntimeError("model returned no loss")
+        (out.loss / self.config['accumulation_steps']).backward()
+        return out.loss.detach()
+
+    def train_epoch(self, epoch):
+        self.model.train()
+        self.epoch = epoch
+        loss_sum = torch.zeros((), device=self.device, dtype=torch.float64)
+        n_samples = 0
+        pending = 0
+        for batch in self.train_loader:
+            loss = self.train_step(batch)
+            pending += 1
+            if pending >= self.config['accumulation_steps']:
+                self._optimizer_step(step_scheduler=True)
+                pending = 0
+            n = len(batch['labels'])
+            loss_sum += loss.double() * n
+            n_samples += n
+        if pending > 0:                      # trainer.py:139-145: flush without scheduler.step()
+            self._optimizer_step(step_scheduler=False)
+        return (loss_sum / n_samples).item() if n_samples else float('inf')

@@ -143,6 +143,25 @@ typedef struct eegx_gemm_desc {
 int eegx_gemm_bf16(const eegx_gemm_desc* desc, const void* A, const void* B, const float* bias,
                    void* D, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Optimizer step of EEGTrainer.train_epoch (main_model/src/training/trainer.py:101-113;
+ * wiring main_model/scripts/train.py:199-241) over flat fp32 buffers.
+ *   eegx_sumsq_f32      out[0] (+)= sum(g^2), two fixed-order stages (bit-stable); with
+ *                       accumulate != 0 several parameter groups add into one global norm.
+ *   eegx_adamw_clip_f32 clip_grad_norm_ coefficient min(1, max_norm / (sqrt(*grad_norm_sq) *
+ *                       grad_scale + 1e-6)) computed on the device (grad_norm_sq may be NULL:
+ *                       no clipping), then torch.optim.AdamW's update:
+ *                         p *= 1 - lr*wd;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2
+ *                         p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+ *                       grad_scale folds a constant factor on g (e.g. 1/world_size).
+ * ------------------------------------------------------------------------ */
+size_t eegx_sumsq_workspace_bytes(void);
+int eegx_sumsq_f32(const float* g, int64_t n, float* out, int accumulate, void* workspace,
+                   size_t workspace_bytes, void* stream);
+int eegx_adamw_clip_f32(float* p, const float* g, float* m, float* v, int64_t n, float lr,
+                        float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                        const float* grad_norm_sq, float max_norm, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
