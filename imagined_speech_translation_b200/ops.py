@@ -10,6 +10,11 @@ from . import _lib
 
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU = 0, 1, 2
 
+# Measurement hook (bench.py): when a list is installed here, every gemm() call is bracketed by
+# CUDA events on the launching stream and (start, end, flops) is appended.
+GEMM_TIMING = None
+LAUNCHES = {"gemm": 0}
+
 
 def _check_bf16(t: torch.Tensor, name: str):
     if not t.is_cuda:
@@ -66,6 +71,13 @@ def gemm(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     d.accumulate = int(accumulate)
     d.force_block_n = int(force_block_n)
     d.alpha = float(alpha)
+    LAUNCHES["gemm"] += 1
+    if GEMM_TIMING is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _lib.check(_lib.lib().eegx_gemm_bf16(C.byref(d), _lib.ptr(a), _lib.ptr(b), _lib.ptr(bias),
                                          _lib.ptr(out), _lib.stream_ptr()), "eegx_gemm_bf16")
+    if GEMM_TIMING is not None:
+        e1.record()
+        GEMM_TIMING.append((e0, e1, 2.0 * M * N * K * batch))
     return out

@@ -65,6 +65,27 @@ def cosine_schedule_with_warmup(optimizer, num_warmup_steps, num_training_steps,
     return torch.optim.lr_scheduler.LambdaLR(optimizer, lr_lambda)
 
 
+def initialize_custom_weights(model):
+    """Initialisation of the non-BART parameters by name substring, as
+    ``scripts/train.py:108-126``: '*weight*' with 'norm' -> 1, with 'embedding' -> N(0, 0.02^2),
+    other weights with >= 2 dims -> xavier_uniform(gain 0.02); '*bias*' -> 0.  Tokens, positional
+    embeddings, region_importance and 1-D BatchNorm / in-Sequential LayerNorm gains keep their
+    constructor values (no 'weight'/'bias' in the name, or 1-D without 'norm')."""
+    for name, p in model.named_parameters():
+        if 'bart' in name.lower():
+            continue
+        if 'weight' in name:
+            if 'norm' in name:
+                torch.nn.init.ones_(p)
+            elif 'embedding' in name:
+                torch.nn.init.normal_(p, std=0.02)
+            elif p.dim() >= 2:
+                torch.nn.init.xavier_uniform_(p, gain=0.02)
+        elif 'bias' in name:
+            torch.nn.init.zeros_(p)
+    return model
+
+
 class EEGTrainer:
     def __init__(self, model, tokenizer, train_loader, val_loader, optimizer, scheduler, config,
                  front_end=None, region_channel_counts=None, process_group=None):
