@@ -90,8 +90,32 @@ class BrainRegionEncoder(nn.Module):
         h = nn_ops.linear(h, layer.linear2.weight, layer.linear2.bias)
         return (x.float() + layer.dropout2(h.float())).to(torch.bfloat16)
 
+    def _region_features(self, eeg_data):
+        """The four region encoders are independent until the stack: run them on four streams
+        (fork / join by events; also legal under CUDA-graph capture), so their many small kernels
+        overlap instead of queueing behind each other (reference: sequential loop,
+        brain_encoder.py:148-150)."""
+        if not getattr(self, "parallel_regions", True):
+            return [self.region_encoders[n](eeg_data[i]) for i, n in enumerate(self.region_names)]
+        cur = torch.cuda.current_stream()
+        if getattr(self, "_streams", None) is None or self._streams[0].device != eeg_data[0].device:
+            self._streams = [torch.cuda.Stream(device=eeg_data[0].device) for _ in self.region_names]
+        start = cur.record_event()
+        feats = []
+        for i, name in enumerate(self.region_names):
+            s = self._streams[i]
+            s.wait_event(start)
+            with torch.cuda.stream(s):
+                eeg_data[i].record_stream(s)
+                f = self.region_encoders[name](eeg_data[i])
+            f.record_stream(cur)
+            feats.append(f)
+        for s in self._streams:
+            cur.wait_event(s.record_event())
+        return feats
+
     def forward(self, eeg_data):
-        feats = [self.region_encoders[name](eeg_data[i]) for i, name in enumerate(self.region_names)]
+        feats = self._region_features(eeg_data)
         x = torch.stack(feats, dim=1)                            # (B, 4, d) fp32
         ms = self.apply_multi_scale_processing(x.to(torch.bfloat16))
         x = x + 0.3 * ms.float()

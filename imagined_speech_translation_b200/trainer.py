@@ -135,9 +135,47 @@ class EEGTrainer:
             self.scheduler.step()
             self.global_step += 1
 
+    # ------------------------------------------------------------------ CUDA graph
+    def capture(self, example_batch, warmup: int = 2):
+        """Capture preprocess + forward + backward of one micro-batch (fixed shapes) into a CUDA
+        graph; later train_step() calls with same-shaped batches copy into the static inputs and
+        replay.  The optimizer step stays outside (its learning rates change every step).
+        Needs the flat gradient buffers to exist, i.e. at least one optimizer step before."""
+        if not isinstance(self.optimizer, FlatAdamW) or self.optimizer._flat is None:
+            raise RuntimeError("run one eager train_step + optimizer step before capture()")
+        self._static = {k: v.to(self.device).clone() for k, v in example_batch.items() if torch.is_tensor(v)}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._eager_step(self._static)
+            self.optimizer.zero_grad()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_loss = self._eager_step(self._static)
+        self.optimizer.zero_grad()
+        return self
+
+    def _eager_step(self, batch):
+        eeg = self._regions(batch)
+        ids = batch['decoder_input_ids'].to(self.device, non_blocking=True)
+        labels = batch['labels'].to(self.device, non_blocking=True)
+        out = self.forward_pass(eeg, ids, labels)
+        if out.loss is None:
+            raise RuntimeError("model returned no loss")
+        (out.loss / self.config['accumulation_steps']).backward()
+        return out.loss.detach()
+
     def train_step(self, batch):
         """One micro-batch: preprocess (if raw) + forward + backward of loss / accumulation_steps.
         Returns the un-scaled loss as a device scalar (no host sync)."""
+        if getattr(self, "_graph", None) is not None:
+            for k, dst in self._static.items():
+                dst.copy_(batch[k], non_blocking=True)
+            self._graph.replay()
+            return self._static_loss
         eeg = self._regions(batch)
         ids = batch['decoder_input_ids'].to(self.device, non_blocking=True)
         labels = batch['labels'].to(self.device, non_blocking=True)

@@ -31,6 +31,11 @@ def step():
 
 for _ in range(3): step()
 torch.cuda.synchronize()
+if os.environ.get("EEGX_GRAPH", "0") == "1":
+    t.capture(batch)
+    for _ in range(2): step()
+    torch.cuda.synchronize()
+    print("captured CUDA graph")
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 n = 5
