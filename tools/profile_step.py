@@ -46,4 +46,7 @@ print(f"B={B}: {ms:.2f} ms/step  {B/ms*1e3:.0f} trials/s  loss {loss.item():.3f}
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     step(); torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=28, max_name_column_width=60))
+tab = prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=70)
+os.makedirs("gpurun_out", exist_ok=True)
+open(os.path.join("gpurun_out", f"step_profile_B{B}.txt"), "w").write(tab)
+print(tab[:6000])
