@@ -63,6 +63,41 @@ SIGNATURES["eegx_adamw_clip_f32"] = (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_
                                                C.c_int64, C.c_void_p, C.c_float, C.c_float, C.c_void_p])
 
 
+class AttnDesc(C.Structure):
+    """Mirror of eegx_attn_desc (include/eegx.h)."""
+    _fields_ = [("B", C.c_int64), ("H", C.c_int64), ("Sq", C.c_int64), ("Sk", C.c_int64), ("hd", C.c_int64),
+                ("q_rs", C.c_int64), ("k_rs", C.c_int64), ("v_rs", C.c_int64), ("o_rs", C.c_int64),
+                ("causal", C.c_int32), ("scale", C.c_float)]
+
+
+_P, _I64, _U32, _F, _I, _SZ = C.c_void_p, C.c_int64, C.c_uint32, C.c_float, C.c_int, C.c_size_t
+_RNG = [_P, _U32, _F]            # rng_state, site, p
+SIGNATURES.update({
+    "eegx_layernorm_fwd_bf16": (_I, [_P, _P, _P, _P, _P, _P, _I64, _I64, _F, _I] + _RNG + [_P]),
+    "eegx_layernorm_bwd_workspace_bytes": (_SZ, [_I64]),
+    "eegx_layernorm_bwd_bf16": (_I, [_P] * 9 + [_P, _SZ, _I64, _I64, _I] + _RNG + [_P]),
+    "eegx_add_dropout_fwd_bf16": (_I, [_P, _P, _P, _I64, _F] + _RNG + [_P]),
+    "eegx_dropout_scale_bf16": (_I, [_P, _P, _I64, _F] + _RNG + [_P]),
+    "eegx_gelu_dropout_fwd_bf16": (_I, [_P, _P, _I64] + _RNG + [_P]),
+    "eegx_gelu_dropout_bwd_bf16": (_I, [_P, _P, _P, _I64] + _RNG + [_P]),
+    "eegx_glu_fwd_bf16": (_I, [_P, _P, _I64, _I64] + _RNG + [_P]),
+    "eegx_glu_bwd_bf16": (_I, [_P, _P, _P, _I64, _I64] + _RNG + [_P]),
+    "eegx_colreduce_workspace_bytes": (_SZ, [_I64]),
+    "eegx_bn_stats_bf16": (_I, [_P, _I64, _I64, _I64, _I64, _F, _P, _P, _P, _P, _F, _P, _SZ, _P]),
+    "eegx_bn_act_fwd_bf16": (_I, [_P] * 10 + [_I, _P, _I64, _I64, _I64, _I64] + _RNG + [_P]),
+    "eegx_bn_act_bwd_bf16": (_I, [_P] * 11 + [_I, _I, _P, _P, _P, _P, _SZ, _I64, _I64, _I64, _I64] + _RNG + [_P]),
+    "eegx_dwconv5_fwd_bf16": (_I, [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _P]),
+    "eegx_dwconv5_bwd_bf16": (_I, [_P, _P, _P, _P, _P, _P, _SZ, _I64, _I64, _I64, _I64, _P]),
+    "eegx_group_mean_bf16": (_I, [_P, _P, _I64, _I64, _I64, _I64, _P]),
+    "eegx_group_mean_bwd_bf16": (_I, [_P, _P, _I64, _I64, _I64, _I64, _I, _P]),
+    "eegx_se_scale_fwd_bf16": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64] + _RNG + [_P]),
+    "eegx_se_scale_bwd_bf16": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64] + _RNG + [_P]),
+    "eegx_nct_to_rows_bf16": (_I, [_P, _I64, _P, _I64, _I64, _I64, _I64, _P]),
+    "eegx_attn_fwd_bf16": (_I, [C.POINTER(AttnDesc), _P, _P, _P, _P, _P] + _RNG + [_P]),
+    "eegx_attn_bwd_bf16": (_I, [C.POINTER(AttnDesc)] + [_P] * 9 + [_I64, _I64, _I64] + _RNG + [_P]),
+})
+
+
 class EegxError(RuntimeError):
     """A libeegx entry point returned a negative status."""
 

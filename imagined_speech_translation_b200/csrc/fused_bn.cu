@@ -1,0 +1,679 @@
+// Glue of the CNN stack of Conv1DWithAttention (main_model/src/models/layers.py:142-178) on
+// channels-last bf16 rows, forward and backward:
+//   BatchNorm1d in train / eval mode over the valid rows (+ the 1x1-conv residual's BatchNorm)
+//   + residual add + exact GELU + dropout + re-zeroing of the per-trial padding rows   (:142-174)
+//   depthwise Conv1d k=5 (groups = channels)                                           (:157)
+//   SqueezeExcite mean over time and the channel re-scaling + dropout                  (:177-178, :288-298)
+//   (B, C, T) fp32 -> guarded channels-last bf16 (the transpose in front of conv1)     (:142)
+//
+// Layout ("guarded rows"): a (B, T, C) activation is stored as rows m = b*Tp + PAD + t of an
+// (M = B*Tp) x C matrix, Tp = T + 2*PAD, whose other rows are zero, with PAD extra zero rows in
+// front of m = 0 and after m = M-1.  A Conv1d is then a GEMM over overlapping rows (gemm_sm100.cu).
+// Kernels take the pointer to row m = 0; "valid(m)" = (m mod Tp) in [PAD, PAD+T).
+//
+// All reductions over rows are two-stage with a fixed summation order (bit-stable, no atomics).
+#include "eegx_common.h"
+#include "fused_common.cuh"
+
+namespace {
+
+using namespace eegx;
+
+struct RowGeom {
+    long long M;   // B * Tp
+    int Tp, lo, hi;  // valid rows: lo <= (m mod Tp) < hi
+    __device__ __forceinline__ bool valid(long long m) const {
+        const int r = (int)(m % Tp);
+        return r >= lo && r < hi;
+    }
+};
+
+constexpr int CR_THREADS = 256;   // 8 warps; a warp covers 64 columns (2 per lane)
+constexpr int CR_COLS = 64;
+
+// ---- column reduction skeleton: each lane owns 2 columns, warps stride over the rows of the
+// CTA's slab, then the 8 warps are summed in order and the CTA partial is written.
+template <int NACC, typename F>
+__device__ __forceinline__ void col_reduce(const RowGeom& g, int C, float* __restrict__ part, F f) {
+    __shared__ float red[CR_THREADS / 32][NACC][CR_COLS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int c = blockIdx.x * CR_COLS + 2 * lane;
+    const long long rows_per = (g.M + gridDim.y - 1) / gridDim.y;
+    const long long m0 = (long long)blockIdx.y * rows_per;
+    const long long m1 = m0 + rows_per < g.M ? m0 + rows_per : g.M;
+    float acc[NACC][2];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k][0] = acc[k][1] = 0.0f;
+    if (c < C) {
+        for (long long m = m0 + wid; m < m1; m += CR_THREADS / 32)
+            if (g.valid(m)) f(m, c, acc);
+    }
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) {
+        red[wid][k][2 * lane] = acc[k][0];
+        red[wid][k][2 * lane + 1] = acc[k][1];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NACC * CR_COLS; i += CR_THREADS) {
+        const int k = i / CR_COLS, cc = i % CR_COLS;
+        if (blockIdx.x * CR_COLS + cc < C) {
+            float t = 0.0f;
+#pragma unroll
+            for (int w = 0; w < CR_THREADS / 32; ++w) t += red[w][k][cc];
+            part[((long long)blockIdx.y * NACC + k) * C + blockIdx.x * CR_COLS + cc] = t;
+        }
+    }
+}
+
+__device__ __forceinline__ float2 ld2(const __nv_bfloat16* p) {
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+}
+
+// ------------------------------------------------------------------ BatchNorm statistics
+__global__ void __launch_bounds__(CR_THREADS)
+bn_stats_partial_kernel(const __nv_bfloat16* __restrict__ y, RowGeom g, int C, float* __restrict__ part) {
+    col_reduce<2>(g, C, part, [&](long long m, int c, float (&acc)[2][2]) {
+        const float2 v = ld2(y + m * C + c);
+        acc[0][0] += v.x; acc[0][1] += v.y;
+        acc[1][0] = fmaf(v.x, v.x, acc[1][0]); acc[1][1] = fmaf(v.y, v.y, acc[1][1]);
+    });
+}
+
+// mean / rstd from the partials (fp64), and the running-statistics update of nn.BatchNorm1d
+// (momentum; running_var takes the unbiased variance).
+__global__ void bn_stats_final_kernel(const float* __restrict__ part, int nslabs, int C, double n_valid, float eps,
+                                      float* __restrict__ mean, float* __restrict__ rstd,
+                                      float* __restrict__ running_mean, float* __restrict__ running_var,
+                                      float momentum) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0, q = 0.0;
+    for (int b = 0; b < nslabs; ++b) {
+        s += (double)part[((long long)b * 2 + 0) * C + c];
+        q += (double)part[((long long)b * 2 + 1) * C + c];
+    }
+    const double mu = s / n_valid;
+    double var = q / n_valid - mu * mu;
+    if (var < 0.0) var = 0.0;
+    mean[c] = (float)mu;
+    rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean != nullptr) {
+        const double unbiased = n_valid > 1.0 ? var * n_valid / (n_valid - 1.0) : var;
+        running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * (float)mu;
+        running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+}
+
+// ------------------------------------------------------------------ BN (+ residual) + GELU + dropout
+struct BnSide {
+    const __nv_bfloat16* x;   // (M, C) rows from m = 0
+    const float* mean;
+    const float* rstd;
+    const float* gamma;
+    const float* beta;
+};
+
+// res_mode: 0 none, 1 identity (r.x added as is), 2 BatchNorm'd residual
+__global__ void __launch_bounds__(256)
+bn_act_fwd_kernel(BnSide a, BnSide r, int res_mode, __nv_bfloat16* __restrict__ out, RowGeom g, int pad, int C,
+                  DropoutCfg dc) {
+    const DropoutGen gen(dc);
+    const int c8 = C >> 3;
+    const long long total = (g.M + 2 * pad) * c8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long m = i / c8 - pad;
+        const int c = (int)(i % c8) * 8;
+        float o[8];
+        if (m >= 0 && m < g.M && g.valid(m)) {
+            float v[8], mu[8], rs[8], ga[8], be[8], msk[8];
+            load8(a.x + m * C + c, v);
+            load8f(a.mean + c, mu); load8f(a.rstd + c, rs); load8f(a.gamma + c, ga); load8f(a.beta + c, be);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = fmaf((v[e] - mu[e]) * rs[e], ga[e], be[e]);
+            if (res_mode == 1) {
+                load8(r.x + m * C + c, v);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] += v[e];
+            } else if (res_mode == 2) {
+                load8(r.x + m * C + c, v);
+                load8f(r.mean + c, mu); load8f(r.rstd + c, rs); load8f(r.gamma + c, ga); load8f(r.beta + c, be);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] += fmaf((v[e] - mu[e]) * rs[e], ga[e], be[e]);
+            }
+            gen.mask8((unsigned long long)(m * C + c) >> 3, msk);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = gelu_f(o[e]) * msk[e];
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = 0.0f;
+        }
+        store8(out + m * C + c, o);
+    }
+}
+
+// dpre = dout * dropout_mask * gelu'(pre), pre = bn(a) + residual; shared by the two backward passes
+__device__ __forceinline__ void bn_act_dpre(const BnSide& a, const BnSide& r, int res_mode,
+                                            const __nv_bfloat16* dout, long long m, int c, int C,
+                                            const DropoutGen& gen, float (&dp)[2], float (&ha)[2], float (&hr)[2]) {
+    const float2 va = ld2(a.x + m * C + c);
+    const float2 d = ld2(dout + m * C + c);
+    ha[0] = (va.x - a.mean[c]) * a.rstd[c];
+    ha[1] = (va.y - a.mean[c + 1]) * a.rstd[c + 1];
+    float pre0 = fmaf(ha[0], a.gamma[c], a.beta[c]), pre1 = fmaf(ha[1], a.gamma[c + 1], a.beta[c + 1]);
+    hr[0] = hr[1] = 0.0f;
+    if (res_mode == 1) {
+        const float2 vr = ld2(r.x + m * C + c);
+        pre0 += vr.x; pre1 += vr.y;
+    } else if (res_mode == 2) {
+        const float2 vr = ld2(r.x + m * C + c);
+        hr[0] = (vr.x - r.mean[c]) * r.rstd[c];
+        hr[1] = (vr.y - r.mean[c + 1]) * r.rstd[c + 1];
+        pre0 += fmaf(hr[0], r.gamma[c], r.beta[c]);
+        pre1 += fmaf(hr[1], r.gamma[c + 1], r.beta[c + 1]);
+    }
+    float m0, m1;
+    gen.mask_pair((unsigned long long)(m * C + c) >> 3, c & 7, m0, m1);
+    dp[0] = d.x * m0 * gelu_grad_f(pre0);
+    dp[1] = d.y * m1 * gelu_grad_f(pre1);
+}
+
+// partial sums per channel: [0] sum dpre, [1] sum dpre * xhat_a, [2] sum dpre * xhat_r
+__global__ void __launch_bounds__(CR_THREADS)
+bn_act_bwd_reduce_kernel(BnSide a, BnSide r, int res_mode, const __nv_bfloat16* __restrict__ dout, RowGeom g, int C,
+                         DropoutCfg dc, float* __restrict__ part) {
+    const DropoutGen gen(dc);
+    col_reduce<3>(g, C, part, [&](long long m, int c, float (&acc)[3][2]) {
+        float dp[2], ha[2], hr[2];
+        bn_act_dpre(a, r, res_mode, dout, m, c, C, gen, dp, ha, hr);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            acc[0][e] += dp[e];
+            acc[1][e] = fmaf(dp[e], ha[e], acc[1][e]);
+            acc[2][e] = fmaf(dp[e], hr[e], acc[2][e]);
+        }
+    });
+}
+
+// sums: (3, C) finished sums.  train != 0: batch-statistics backward; train == 0 (eval): the
+// statistics are constants, dy = dpre * gamma * rstd.
+// da / dr: rows m in [-pad, M + pad) are all written (zeros outside the valid rows).
+__global__ void __launch_bounds__(256)
+bn_act_bwd_apply_kernel(BnSide a, BnSide r, int res_mode, const __nv_bfloat16* __restrict__ dout,
+                        const float* __restrict__ sums, float inv_n, int train, __nv_bfloat16* __restrict__ da,
+                        __nv_bfloat16* __restrict__ dr, RowGeom g, int pad, int C, DropoutCfg dc) {
+    const DropoutGen gen(dc);
+    const int c2 = C >> 1;
+    const long long total = (g.M + 2 * pad) * c2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long m = i / c2 - pad;
+        const int c = (int)(i % c2) * 2;
+        float oa[2] = {0.0f, 0.0f}, orr[2] = {0.0f, 0.0f};
+        if (m >= 0 && m < g.M && g.valid(m)) {
+            float dp[2], ha[2], hr[2];
+            bn_act_dpre(a, r, res_mode, dout, m, c, C, gen, dp, ha, hr);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const float s1 = train ? sums[c + e] * inv_n : 0.0f;
+                const float s2a = train ? sums[C + c + e] * inv_n : 0.0f;
+                oa[e] = a.gamma[c + e] * a.rstd[c + e] * (dp[e] - s1 - ha[e] * s2a);
+                if (res_mode == 1) {
+                    orr[e] = dp[e];
+                } else if (res_mode == 2) {
+                    const float s2r = train ? sums[2 * C + c + e] * inv_n : 0.0f;
+                    orr[e] = r.gamma[c + e] * r.rstd[c + e] * (dp[e] - s1 - hr[e] * s2r);
+                }
+            }
+        }
+        *reinterpret_cast<__nv_bfloat162*>(da + m * C + c) = __floats2bfloat162_rn(oa[0], oa[1]);
+        if (res_mode != 0) *reinterpret_cast<__nv_bfloat162*>(dr + m * C + c) = __floats2bfloat162_rn(orr[0], orr[1]);
+    }
+}
+
+// out[k][c] = sum over slabs of part[slab][k][c]
+__global__ void sum_partials_kernel(const float* __restrict__ part, int nslabs, int nacc, int C,
+                                    float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    for (int k = 0; k < nacc; ++k) {
+        float t = 0.0f;
+        for (int b = 0; b < nslabs; ++b) t += part[((long long)b * nacc + k) * C + c];
+        out[(long long)k * C + c] = t;
+    }
+}
+
+// ------------------------------------------------------------------ depthwise Conv1d, k = 5
+// w: (C, 5) fp32 (nn.Conv1d weight (C, 1, 5)), bias (C).  x, out: guarded rows.
+__global__ void __launch_bounds__(256)
+dwconv5_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                   __nv_bfloat16* __restrict__ out, RowGeom g, int pad, int C) {
+    const int c8 = C >> 3;
+    const long long total = (g.M + 2 * pad) * c8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long m = i / c8 - pad;
+        const int c = (int)(i % c8) * 8;
+        float o[8];
+        if (m >= 0 && m < g.M && g.valid(m)) {
+            load8f(bias + c, o);
+#pragma unroll
+            for (int tap = 0; tap < 5; ++tap) {
+                float v[8];
+                load8(x + (m + tap - 2) * C + c, v);     // rows m-2..m+2 exist (pad >= 2) and are zero outside trials
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = fmaf(v[e], w[(c + e) * 5 + tap], o[e]);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = 0.0f;
+        }
+        store8(out + m * C + c, o);
+    }
+}
+
+// dx[m] = sum_tap w[tap] * dout[m - tap + 2]; dout is (M, C) from m = 0, zero on invalid rows
+// (rows outside [0, M) are treated as zero); dx: guarded, all rows written, zero on invalid rows.
+__global__ void __launch_bounds__(256)
+dwconv5_bwd_data_kernel(const __nv_bfloat16* __restrict__ dout, const float* __restrict__ w,
+                        __nv_bfloat16* __restrict__ dx, RowGeom g, int pad, int C) {
+    const int c8 = C >> 3;
+    const long long total = (g.M + 2 * pad) * c8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long m = i / c8 - pad;
+        const int c = (int)(i % c8) * 8;
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = 0.0f;
+        if (m >= 0 && m < g.M && g.valid(m)) {
+#pragma unroll
+            for (int tap = 0; tap < 5; ++tap) {
+                const long long mm = m - tap + 2;
+                if (mm >= 0 && mm < g.M) {
+                    float v[8];
+                    load8(dout + mm * C + c, v);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] = fmaf(v[e], w[(c + e) * 5 + tap], o[e]);
+                }
+            }
+        }
+        store8(dx + m * C + c, o);
+    }
+}
+
+// partials: [tap] sum_m dout[m] * x[m + tap - 2] (tap 0..4), [5] sum_m dout[m]
+__global__ void __launch_bounds__(CR_THREADS)
+dwconv5_bwd_weight_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ x, RowGeom g,
+                          int C, float* __restrict__ part) {
+    col_reduce<6>(g, C, part, [&](long long m, int c, float (&acc)[6][2]) {
+        const float2 d = ld2(dout + m * C + c);
+#pragma unroll
+        for (int tap = 0; tap < 5; ++tap) {
+            const float2 v = ld2(x + (m + tap - 2) * C + c);
+            acc[tap][0] = fmaf(d.x, v.x, acc[tap][0]);
+            acc[tap][1] = fmaf(d.y, v.y, acc[tap][1]);
+        }
+        acc[5][0] += d.x; acc[5][1] += d.y;
+    });
+}
+
+// ------------------------------------------------------------------ SqueezeExcite pieces
+// s[b][c] = (1/T) sum_t x[b, t, c]  (fp32); one CTA per (trial, 64 columns)
+__global__ void __launch_bounds__(256)
+group_mean_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ s, int Tp, int lo, int hi, int C) {
+    __shared__ float red[8][CR_COLS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int c = blockIdx.x * CR_COLS + 2 * lane;
+    const long long base = (long long)blockIdx.y * Tp;
+    float a0 = 0.0f, a1 = 0.0f;
+    if (c < C)
+        for (int t = lo + wid; t < hi; t += 8) {
+            const float2 v = ld2(x + (base + t) * C + c);
+            a0 += v.x; a1 += v.y;
+        }
+    red[wid][2 * lane] = a0;
+    red[wid][2 * lane + 1] = a1;
+    __syncthreads();
+    if (threadIdx.x < CR_COLS && blockIdx.x * CR_COLS + threadIdx.x < C) {
+        float t = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+        s[(long long)blockIdx.y * C + blockIdx.x * CR_COLS + threadIdx.x] = t / (float)(hi - lo);
+    }
+}
+
+// ds (B, C) fp32 -> dx rows: dx[b, t, c] = ds[b, c] / T on valid rows (rows from m = 0; only valid rows written)
+// fused with the SE scaling backward below via `dscale`.
+// out[(b*T + t), c] = x[b, lo + t, c] * e[b, c] * dropout   (compact rows, bf16)
+__global__ void __launch_bounds__(256)
+se_scale_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ e, __nv_bfloat16* __restrict__ out,
+                    long long B, int T, int Tp, int lo, int C, DropoutCfg dc) {
+    const DropoutGen gen(dc);
+    const int c8 = C >> 3;
+    const long long total = B * T * c8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / c8;
+        const int c = (int)(i % c8) * 8;
+        const long long b = row / T;
+        const int t = (int)(row % T);
+        float v[8], ev[8], m[8], o[8];
+        load8(x + (b * Tp + lo + t) * C + c, v);
+        load8f(e + b * C + c, ev);
+        gen.mask8((unsigned long long)i, m);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = v[k] * ev[k] * m[k];
+        store8(out + row * C + c, o);
+    }
+}
+
+// dx[b, lo + t, c] = dout[(b*T+t), c] * mask * e[b, c]   (valid rows only are written)
+__global__ void __launch_bounds__(256)
+se_scale_bwd_x_kernel(const __nv_bfloat16* __restrict__ dout, const float* __restrict__ e,
+                      __nv_bfloat16* __restrict__ dx, long long B, int T, int Tp, int lo, int C, DropoutCfg dc) {
+    const DropoutGen gen(dc);
+    const int c8 = C >> 3;
+    const long long total = B * T * c8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / c8;
+        const int c = (int)(i % c8) * 8;
+        const long long b = row / T;
+        const int t = (int)(row % T);
+        float d[8], ev[8], m[8], o[8];
+        load8(dout + row * C + c, d);
+        load8f(e + b * C + c, ev);
+        gen.mask8((unsigned long long)i, m);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = d[k] * ev[k] * m[k];
+        store8(dx + (b * Tp + lo + t) * C + c, o);
+    }
+}
+
+// de[b][c] = sum_t dout[(b*T+t), c] * mask * x[b, lo + t, c]; one CTA per (trial, 64 columns)
+__global__ void __launch_bounds__(256)
+se_scale_bwd_e_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ x,
+                      float* __restrict__ de, int T, int Tp, int lo, int C, DropoutCfg dc) {
+    __shared__ float red[8][CR_COLS];
+    const DropoutGen gen(dc);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int c = blockIdx.x * CR_COLS + 2 * lane;
+    const long long b = blockIdx.y;
+    const int c8 = C >> 3;
+    float a0 = 0.0f, a1 = 0.0f;
+    if (c < C)
+        for (int t = wid; t < T; t += 8) {
+            const float2 d = ld2(dout + (b * T + t) * C + c);
+            const float2 v = ld2(x + (b * Tp + lo + t) * C + c);
+            float m0, m1;
+            gen.mask_pair((unsigned long long)((b * T + t) * c8 + (c >> 3)), c & 7, m0, m1);
+            a0 = fmaf(d.x * m0, v.x, a0);
+            a1 = fmaf(d.y * m1, v.y, a1);
+        }
+    red[wid][2 * lane] = a0;
+    red[wid][2 * lane + 1] = a1;
+    __syncthreads();
+    if (threadIdx.x < CR_COLS && blockIdx.x * CR_COLS + threadIdx.x < C) {
+        float t = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+        de[b * C + blockIdx.x * CR_COLS + threadIdx.x] = t;
+    }
+}
+
+// dx[b, lo + t, c] (+)= ds[b, c] / T on the valid rows (backward of group_mean)
+__global__ void __launch_bounds__(256)
+group_mean_bwd_kernel(const float* __restrict__ ds, __nv_bfloat16* __restrict__ dx, long long B, int T, int Tp,
+                      int lo, int C, int accumulate) {
+    const int c8 = C >> 3;
+    const long long total = B * T * c8;
+    const float inv_t = 1.0f / (float)T;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / c8;
+        const int c = (int)(i % c8) * 8;
+        const long long b = row / T;
+        const int t = (int)(row % T);
+        float d[8], o[8];
+        load8f(ds + b * C + c, d);
+        __nv_bfloat16* dst = dx + (b * Tp + lo + t) * C + c;
+        if (accumulate) {
+            load8(dst, o);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = fmaf(d[k], inv_t, o[k]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = d[k] * inv_t;
+        }
+        store8(dst, o);
+    }
+}
+
+// ------------------------------------------------------------------ (B, C, T) fp32 -> guarded channels-last bf16
+// x: trial b at x + b * x_bstride, (C, T) contiguous.  out rows m in [-pad, M + pad) all written.
+constexpr int TR_C = 64, TR_T = 32;
+__global__ void __launch_bounds__(256)
+nct_to_rows_kernel(const float* __restrict__ x, long long x_bstride, __nv_bfloat16* __restrict__ out, int T,
+                   int Tp, int lo, int C) {
+    __shared__ float tile[TR_C][TR_T + 1];
+    const long long b = blockIdx.z;
+    const int c0 = blockIdx.x * TR_C, t0 = blockIdx.y * TR_T;
+    const float* src = x + b * x_bstride;
+    for (int i = threadIdx.x; i < TR_C * TR_T; i += 256) {
+        const int cc = i / TR_T, tt = i % TR_T;
+        const int c = c0 + cc, t = t0 + tt;
+        tile[cc][tt] = (c < C && t < T) ? src[(long long)c * T + t] : 0.0f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < TR_T * (TR_C / 2); i += 256) {
+        const int tt = i / (TR_C / 2), cc = (i % (TR_C / 2)) * 2;
+        const int c = c0 + cc, t = t0 + tt;
+        if (c < C && t < T)
+            *reinterpret_cast<__nv_bfloat162*>(out + (b * Tp + lo + t) * C + c) =
+                __floats2bfloat162_rn(tile[cc][tt], tile[cc + 1][tt]);
+    }
+}
+
+// zero the rows of a guarded buffer that are not valid (padding rows inside [0, M) and the guards)
+__global__ void __launch_bounds__(256)
+zero_invalid_rows_kernel(__nv_bfloat16* __restrict__ out, RowGeom g, int pad, int C) {
+    const int c8 = C >> 3;
+    const long long total = (g.M + 2 * pad) * c8;
+    const float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long m = i / c8 - pad;
+        const int c = (int)(i % c8) * 8;
+        if (!(m >= 0 && m < g.M && g.valid(m))) store8(out + m * C + c, z);
+    }
+}
+
+int ew_grid(long long n) {
+    long long b = (n + 255) / 256;
+    const long long cap = (long long)kNumSMsB200 * 8;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+int slabs_for(long long M, int C) {
+    const int colblocks = (C + CR_COLS - 1) / CR_COLS;
+    long long s = (2LL * kNumSMsB200 + colblocks - 1) / colblocks;
+    const long long max_by_rows = (M + 31) / 32;
+    if (s > max_by_rows) s = max_by_rows;
+    if (s < 1) s = 1;
+    if (s > 64) s = 64;
+    return (int)s;
+}
+
+}  // namespace
+
+#define EEGX_GEOM_CHECK(name)                                                                                  \
+    if (int rc = eegx::require_sm100()) return rc;                                                             \
+    EEGX_REQUIRE(B >= 0 && T >= 1 && pad >= 2 && C >= 8 && (C % 8) == 0, EEGX_ERR_SHAPE,                       \
+                 name ": need T >= 1, pad >= 2, C a multiple of 8");                                           \
+    const RowGeom g{(long long)B * (T + 2 * pad), (int)(T + 2 * pad), (int)pad, (int)(pad + T)};               \
+    cudaStream_t st = static_cast<cudaStream_t>(stream);                                                       \
+    (void)st
+
+extern "C" {
+
+size_t eegx_colreduce_workspace_bytes(int64_t C) { return (size_t)64 * 6 * (size_t)C * sizeof(float); }
+
+int eegx_bn_stats_bf16(const void* y, int64_t B, int64_t T, int64_t pad, int64_t C, float eps, float* mean,
+                       float* rstd, float* running_mean, float* running_var, float momentum, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+    EEGX_GEOM_CHECK("bn_stats");
+    if (B == 0) return EEGX_OK;
+    EEGX_REQUIRE(y && mean && rstd && workspace, EEGX_ERR_ARG, "bn_stats: NULL pointer");
+    EEGX_REQUIRE(workspace_bytes >= eegx_colreduce_workspace_bytes(C), EEGX_ERR_WORKSPACE, "bn_stats: workspace too small");
+    const int slabs = slabs_for(g.M, (int)C);
+    float* part = static_cast<float*>(workspace);
+    dim3 grid((unsigned)((C + CR_COLS - 1) / CR_COLS), (unsigned)slabs);
+    bn_stats_partial_kernel<<<grid, CR_THREADS, 0, st>>>(static_cast<const __nv_bfloat16*>(y), g, (int)C, part);
+    bn_stats_final_kernel<<<(int)((C + 127) / 128), 128, 0, st>>>(part, slabs, (int)C, (double)B * (double)T, eps, mean,
+                                                                  rstd, running_mean, running_var, momentum);
+    EEGX_CUDA_CHECK(cudaGetLastError());
+    return EEGX_OK;
+}
+
+int eegx_bn_act_fwd_bf16(const void* ya, const float* mean_a, const float* rstd_a, const float* gamma_a,
+                         const float* beta_a, const void* yr, const float* mean_r, const float* rstd_r,
+                         const float* gamma_r, const float* beta_r, int res_mode, void* out, int64_t B, int64_t T,
+                         int64_t pad, int64_t C, const uint64_t* rng_state, uint32_t site, float p, void* stream) {
+    EEGX_GEOM_CHECK("bn_act_fwd");
+    if (B == 0) return EEGX_OK;
+    EEGX_REQUIRE(ya && mean_a && rstd_a && gamma_a && beta_a && out, EEGX_ERR_ARG, "bn_act_fwd: NULL pointer");
+    EEGX_REQUIRE(res_mode == 0 || yr, EEGX_ERR_ARG, "bn_act_fwd: residual pointer missing");
+    EEGX_REQUIRE(res_mode != 2 || (mean_r && rstd_r && gamma_r && beta_r), EEGX_ERR_ARG,
+                 "bn_act_fwd: residual statistics missing");
+    const BnSide a{static_cast<const __nv_bfloat16*>(ya), mean_a, rstd_a, gamma_a, beta_a};
+    const BnSide r{static_cast<const __nv_bfloat16*>(yr), mean_r, rstd_r, gamma_r, beta_r};
+    const DropoutCfg dc{reinterpret_cast<const unsigned long long*>(rng_state), site, p};
+    bn_act_fwd_kernel<<<ew_grid((g.M + 2 * pad) * (C / 8)), 256, 0, st>>>(a, r, res_mode, static_cast<__nv_bfloat16*>(out),
+                                                                          g, (int)pad, (int)C, dc);
+    EEGX_CUDA_CHECK(cudaGetLastError());
+    return EEGX_OK;
+}
+
+/* sums: (3, C) fp32 out: [0] dbeta (both sides), [1] dgamma_a, [2] dgamma_r.  da / dr: guarded buffers
+ * (pointer to row m = 0), every row written. */
+int eegx_bn_act_bwd_bf16(const void* dout, const void* ya, const float* mean_a, const float* rstd_a,
+                         const float* gamma_a, const float* beta_a, const void* yr, const float* mean_r,
+                         const float* rstd_r, const float* gamma_r, const float* beta_r, int res_mode, int train,
+                         void* da, void* dr, float* sums, void* workspace, size_t workspace_bytes, int64_t B,
+                         int64_t T, int64_t pad, int64_t C, const uint64_t* rng_state, uint32_t site, float p,
+                         void* stream) {
+    EEGX_GEOM_CHECK("bn_act_bwd");
+    if (B == 0) return EEGX_OK;
+    EEGX_REQUIRE(dout && ya && mean_a && rstd_a && gamma_a && beta_a && da && sums && workspace, EEGX_ERR_ARG,
+                 "bn_act_bwd: NULL pointer");
+    EEGX_REQUIRE(res_mode == 0 || (yr && dr), EEGX_ERR_ARG, "bn_act_bwd: residual pointers missing");
+    EEGX_REQUIRE(workspace_bytes >= eegx_colreduce_workspace_bytes(C), EEGX_ERR_WORKSPACE, "bn_act_bwd: workspace too small");
+    const BnSide a{static_cast<const __nv_bfloat16*>(ya), mean_a, rstd_a, gamma_a, beta_a};
+    const BnSide r{static_cast<const __nv_bfloat16*>(yr), mean_r, rstd_r, gamma_r, beta_r};
+    const DropoutCfg dc{reinterpret_cast<const unsigned long long*>(rng_state), site, p};
+    const int slabs = slabs_for(g.M, (int)C);
+    float* part = static_cast<float*>(workspace);
+    dim3 grid((unsigned)((C + CR_COLS - 1) / CR_COLS), (unsigned)slabs);
+    bn_act_bwd_reduce_kernel<<<grid, CR_THREADS, 0, st>>>(a, r, res_mode, static_cast<const __nv_bfloat16*>(dout), g,
+                                                          (int)C, dc, part);
+    sum_partials_kernel<<<(int)((C + 127) / 128), 128, 0, st>>>(part, slabs, 3, (int)C, sums);
+    bn_act_bwd_apply_kernel<<<ew_grid((g.M + 2 * pad) * (C / 2)), 256, 0, st>>>(
+        a, r, res_mode, static_cast<const __nv_bfloat16*>(dout), sums, 1.0f / (float)((double)B * (double)T), train,
+        static_cast<__nv_bfloat16*>(da), static_cast<__nv_bfloat16*>(dr), g, (int)pad, (int)C, dc);
+    EEGX_CUDA_CHECK(cudaGetLastError());
+    return EEGX_OK;
+}
+
+int eegx_dwconv5_fwd_bf16(const void* x, const float* w, const float* bias, void* out, int64_t B, int64_t T,
+                          int64_t pad, int64_t C, void* stream) {
+    EEGX_GEOM_CHECK("dwconv5_fwd");
+    if (B == 0) return EEGX_OK;
+    EEGX_REQUIRE(x && w && bias && out, EEGX_ERR_ARG, "dwconv5_fwd: NULL pointer");
+    dwconv5_fwd_kernel<<<ew_grid((g.M + 2 * pad) * (C / 8)), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(x), w, bias, static_cast<__nv_bfloat16*>(out), g, (int)pad, (int)C);
+    EEGX_CUDA_CHECK(cudaGetLastError());
+    return EEGX_OK;
+}
+
+/* dw: (C, 5) fp32, db: (C) fp32.  dwdb_scratch: (6, C) fp32. */
+int eegx_dwconv5_bwd_bf16(const void* dout, const void* x, const float* w, void* dx, float* dwdb_scratch,
+                          void* workspace, size_t workspace_bytes, int64_t B, int64_t T, int64_t pad, int64_t C,
+                          void* stream) {
+    EEGX_GEOM_CHECK("dwconv5_bwd");
+    if (B == 0) return EEGX_OK;
+    EEGX_REQUIRE(dout && x && w && dx && dwdb_scratch && workspace, EEGX_ERR_ARG, "dwconv5_bwd: NULL pointer");
+    EEGX_REQUIRE(workspace_bytes >= eegx_colreduce_workspace_bytes(C), EEGX_ERR_WORKSPACE, "dwconv5_bwd: workspace too small");
+    dwconv5_bwd_data_kernel<<<ew_grid((g.M + 2 * pad) * (C / 8)), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(dout), w, static_cast<__nv_bfloat16*>(dx), g, (int)pad, (int)C);
+    const int slabs = slabs_for(g.M, (int)C);
+    float* part = static_cast<float*>(workspace);
+    dim3 grid((unsigned)((C + CR_COLS - 1) / CR_COLS), (unsigned)slabs);
+    dwconv5_bwd_weight_kernel<<<grid, CR_THREADS, 0, st>>>(static_cast<const __nv_bfloat16*>(dout),
+                                                           static_cast<const __nv_bfloat16*>(x), g, (int)C, part);
+    sum_partials_kernel<<<(int)((C + 127) / 128), 128, 0, st>>>(part, slabs, 6, (int)C, dwdb_scratch);
+    EEGX_CUDA_CHECK(cudaGetLastError());
+    return EEGX_OK;
+}
+
+int eegx_group_mean_bf16(const void* x, float* s, int64_t B, int64_t T, int64_t pad, int64_t C, void* stream) {
+    EEGX_GEOM_CHECK("group_mean");
+    if (B == 0) return EEGX_OK;
+    EEGX_REQUIRE(x && s, EEGX_ERR_ARG, "group_mean: NULL pointer");
+    dim3 grid((unsigned)((C + CR_COLS - 1) / CR_COLS), (unsigned)B);
+    group_mean_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), s, g.Tp, g.lo, g.hi, (int)C);
+    EEGX_CUDA_CHECK(cudaGetLastError());
+    return EEGX_OK;
+}
+
+int eegx_group_mean_bwd_bf16(const float* ds, void* dx, int64_t B, int64_t T, int64_t pad, int64_t C,
+                             int accumulate, void* stream) {
+    EEGX_GEOM_CHECK("group_mean_bwd");
+    if (B == 0) return EEGX_OK;
+    EEGX_REQUIRE(ds && dx, EEGX_ERR_ARG, "group_mean_bwd: NULL pointer");
+    group_mean_bwd_kernel<<<ew_grid(B * T * (C / 8)), 256, 0, st>>>(ds, static_cast<__nv_bfloat16*>(dx), B, (int)T, g.Tp,
+                                                                    g.lo, (int)C, accumulate);
+    EEGX_CUDA_CHECK(cudaGetLastError());
+    return EEGX_OK;
+}
+
+int eegx_se_scale_fwd_bf16(const void* x, const float* e, void* out, int64_t B, int64_t T, int64_t pad, int64_t C,
+                           const uint64_t* rng_state, uint32_t site, float p, void* stream) {
+    EEGX_GEOM_CHECK("se_scale_fwd");
+    if (B == 0) return EEGX_OK;
+    EEGX_REQUIRE(x && e && out, EEGX_ERR_ARG, "se_scale_fwd: NULL pointer");
+    const DropoutCfg dc{reinterpret_cast<const unsigned long long*>(rng_state), site, p};
+    se_scale_fwd_kernel<<<ew_grid(B * T * (C / 8)), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), e,
+                                                                  static_cast<__nv_bfloat16*>(out), B, (int)T, g.Tp, g.lo,
+                                                                  (int)C, dc);
+    EEGX_CUDA_CHECK(cudaGetLastError());
+    return EEGX_OK;
+}
+
+/* dx: guarded rows pointer (m = 0), only the valid rows are written; de: (B, C) fp32. */
+int eegx_se_scale_bwd_bf16(const void* dout, const void* x, const float* e, void* dx, float* de, int64_t B,
+                           int64_t T, int64_t pad, int64_t C, const uint64_t* rng_state, uint32_t site, float p,
+                           void* stream) {
+    EEGX_GEOM_CHECK("se_scale_bwd");
+    if (B == 0) return EEGX_OK;
+    EEGX_REQUIRE(dout && x && e && dx && de, EEGX_ERR_ARG, "se_scale_bwd: NULL pointer");
+    const DropoutCfg dc{reinterpret_cast<const unsigned long long*>(rng_state), site, p};
+    se_scale_bwd_x_kernel<<<ew_grid(B * T * (C / 8)), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dout), e,
+                                                                    static_cast<__nv_bfloat16*>(dx), B, (int)T, g.Tp,
+                                                                    g.lo, (int)C, dc);
+    dim3 grid((unsigned)((C + CR_COLS - 1) / CR_COLS), (unsigned)B);
+    se_scale_bwd_e_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dout),
+                                                static_cast<const __nv_bfloat16*>(x), de, (int)T, g.Tp, g.lo, (int)C, dc);
+    EEGX_CUDA_CHECK(cudaGetLastError());
+    return EEGX_OK;
+}
+
+/* x: (B, C, T) fp32 with batch stride x_bstride (elements); out: guarded rows pointer (m = 0); every row of
+ * the guarded buffer is written (zeros outside the valid rows). */
+int eegx_nct_to_rows_bf16(const float* x, int64_t x_bstride, void* out, int64_t B, int64_t T, int64_t pad,
+                          int64_t C, void* stream) {
+    EEGX_GEOM_CHECK("nct_to_rows");
+    if (B == 0) return EEGX_OK;
+    EEGX_REQUIRE(x && out, EEGX_ERR_ARG, "nct_to_rows: NULL pointer");
+    EEGX_REQUIRE(B <= 65535, EEGX_ERR_SHAPE, "nct_to_rows: B must be <= 65535");
+    zero_invalid_rows_kernel<<<ew_grid((g.M + 2 * pad) * (C / 8)), 256, 0, st>>>(static_cast<__nv_bfloat16*>(out), g,
+                                                                                  (int)pad, (int)C);
+    dim3 grid((unsigned)((C + TR_C - 1) / TR_C), (unsigned)((T + TR_T - 1) / TR_T), (unsigned)B);
+    nct_to_rows_kernel<<<grid, 256, 0, st>>>(x, x_bstride, static_cast<__nv_bfloat16*>(out), (int)T, g.Tp, g.lo, (int)C);
+    EEGX_CUDA_CHECK(cudaGetLastError());
+    return EEGX_OK;
+}
+
+}  // extern "C"

@@ -162,6 +162,114 @@ int eegx_adamw_clip_f32(float* p, const float* g, float* m, float* v, int64_t n,
                         float beta1, float beta2, float eps, float weight_decay, int64_t step,
                         const float* grad_norm_sq, float max_norm, float grad_scale, void* stream);
 
+
+/* ------------------------------------------------------------------------
+ * Fused glue of the encoder (bf16 activations, fp32 parameters / statistics, fp32 math).
+ * Every entry point is one (or two) HBM-bound passes replacing a chain of element-wise
+ * library kernels of the reference modules; forward and backward are separate calls so
+ * torch.autograd.Function wrappers can own the tape.
+ *
+ * Dropout: (rng_state, site, p).  rng_state -> two device uint64 {seed, step}; the keep-mask
+ * of element group i at call site `site` is Philox-4x32-10(seed, step, site, i), regenerated
+ * in backward (no mask tensor).  rng_state == NULL or p == 0 disables dropout.
+ *
+ * "Guarded rows" (CNN stack): a (B, T, C) activation is rows m = b*(T+2*pad) + pad + t of an
+ * (M = B*(T+2*pad)) x C matrix whose other rows are zero, with `pad` more zero rows before
+ * m = 0 and after m = M-1, so nn.Conv1d is a GEMM over overlapping rows.  Pointers address row
+ * m = 0; "out" buffers of this kind have every row (guards included) written.
+ * ------------------------------------------------------------------------ */
+
+/* nn.LayerNorm(C) (+ nn.GELU if act = 1) (+ nn.Dropout) on (rows, C) bf16
+ * (main_model/src/models/layers.py:61-71, 84-127, 232, 240).  mean / rstd: (rows) fp32 saved for backward. */
+int eegx_layernorm_fwd_bf16(const void* x, const float* gamma, const float* beta, void* y, float* mean,
+                            float* rstd, int64_t rows, int64_t C, float eps, int act, const uint64_t* rng_state,
+                            uint32_t site, float p, void* stream);
+size_t eegx_layernorm_bwd_workspace_bytes(int64_t C);
+int eegx_layernorm_bwd_bf16(const void* dy, const void* x, const float* gamma, const float* beta,
+                            const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
+                            void* workspace, size_t workspace_bytes, int64_t rows, int64_t C, int act,
+                            const uint64_t* rng_state, uint32_t site, float p, void* stream);
+
+/* out = a + scale * dropout(b): the residual adds of layers.py:234, 242, 251 / brain_encoder.py:165. */
+int eegx_add_dropout_fwd_bf16(const void* a, const void* b, void* out, int64_t n, float scale,
+                              const uint64_t* rng_state, uint32_t site, float p, void* stream);
+/* out = scale * dropout_mask * in (the backward of the `b` operand above; also a plain dropout). */
+int eegx_dropout_scale_bf16(const void* in, void* out, int64_t n, float scale, const uint64_t* rng_state,
+                            uint32_t site, float p, void* stream);
+/* out = dropout(gelu(x)) (nn.GELU + nn.Dropout after a Linear, brain_encoder.py:36-75) and its backward. */
+int eegx_gelu_dropout_fwd_bf16(const void* x, void* out, int64_t n, const uint64_t* rng_state, uint32_t site,
+                               float p, void* stream);
+int eegx_gelu_dropout_bwd_bf16(const void* dout, const void* x, void* dx, int64_t n, const uint64_t* rng_state,
+                               uint32_t site, float p, void* stream);
+/* FeedForwardNetwork gate (layers.py:311-317): ag = [W1 x | Wg x] (rows, 2H) -> dropout(gelu(a) * sigmoid(g)). */
+int eegx_glu_fwd_bf16(const void* ag, void* out, int64_t rows, int64_t H, const uint64_t* rng_state,
+                      uint32_t site, float p, void* stream);
+int eegx_glu_bwd_bf16(const void* dout, const void* ag, void* dag, int64_t rows, int64_t H,
+                      const uint64_t* rng_state, uint32_t site, float p, void* stream);
+
+/* BatchNorm1d statistics over the valid rows of a conv output (layers.py:31-48; train mode):
+ * mean / rstd (C) fp32; running_mean / running_var updated in place with `momentum` (unbiased
+ * variance) unless NULL.  Two fixed-order stages (bit-stable). */
+size_t eegx_colreduce_workspace_bytes(int64_t C);
+int eegx_bn_stats_bf16(const void* y, int64_t B, int64_t T, int64_t pad, int64_t C, float eps, float* mean,
+                       float* rstd, float* running_mean, float* running_var, float momentum, void* workspace,
+                       size_t workspace_bytes, void* stream);
+/* out = zero_pad_rows( dropout( gelu( bn_a(ya) + residual ) ) )  (layers.py:142-174)
+ * res_mode 0: none; 1: identity residual yr; 2: bn_r(yr) (the 1x1-conv + BatchNorm residual). */
+int eegx_bn_act_fwd_bf16(const void* ya, const float* mean_a, const float* rstd_a, const float* gamma_a,
+                         const float* beta_a, const void* yr, const float* mean_r, const float* rstd_r,
+                         const float* gamma_r, const float* beta_r, int res_mode, void* out, int64_t B, int64_t T,
+                         int64_t pad, int64_t C, const uint64_t* rng_state, uint32_t site, float p, void* stream);
+/* Backward of the above.  sums (3, C) fp32: [0] dbeta (both sides), [1] dgamma_a, [2] dgamma_r.
+ * da / dr: gradients w.r.t. ya / yr as guarded rows.  train = 0: statistics are constants (eval). */
+int eegx_bn_act_bwd_bf16(const void* dout, const void* ya, const float* mean_a, const float* rstd_a,
+                         const float* gamma_a, const float* beta_a, const void* yr, const float* mean_r,
+                         const float* rstd_r, const float* gamma_r, const float* beta_r, int res_mode, int train,
+                         void* da, void* dr, float* sums, void* workspace, size_t workspace_bytes, int64_t B,
+                         int64_t T, int64_t pad, int64_t C, const uint64_t* rng_state, uint32_t site, float p,
+                         void* stream);
+/* Depthwise Conv1d k = 5, groups = C (layers.py:157) on guarded rows; w (C, 5), bias (C) fp32.
+ * Backward: dx guarded rows; dwdb (6, C) fp32 = [dw tap 0..4, dbias]. */
+int eegx_dwconv5_fwd_bf16(const void* x, const float* w, const float* bias, void* out, int64_t B, int64_t T,
+                          int64_t pad, int64_t C, void* stream);
+int eegx_dwconv5_bwd_bf16(const void* dout, const void* x, const float* w, void* dx, float* dwdb,
+                          void* workspace, size_t workspace_bytes, int64_t B, int64_t T, int64_t pad, int64_t C,
+                          void* stream);
+/* SqueezeExciteBlock (layers.py:288-298): s = mean_t x (B, C) fp32; out = dropout(x * e[b, c]) written as
+ * compact (B*T, C) rows; backward: dx (valid guarded rows) and de (B, C). */
+int eegx_group_mean_bf16(const void* x, float* s, int64_t B, int64_t T, int64_t pad, int64_t C, void* stream);
+int eegx_group_mean_bwd_bf16(const float* ds, void* dx, int64_t B, int64_t T, int64_t pad, int64_t C,
+                             int accumulate, void* stream);
+int eegx_se_scale_fwd_bf16(const void* x, const float* e, void* out, int64_t B, int64_t T, int64_t pad, int64_t C,
+                           const uint64_t* rng_state, uint32_t site, float p, void* stream);
+int eegx_se_scale_bwd_bf16(const void* dout, const void* x, const float* e, void* dx, float* de, int64_t B,
+                           int64_t T, int64_t pad, int64_t C, const uint64_t* rng_state, uint32_t site, float p,
+                           void* stream);
+/* (B, C, T) fp32 (batch stride x_bstride elements) -> guarded channels-last bf16 rows: the layout change in
+ * front of conv1 (layers.py:142 consumes (B, C, T)). */
+int eegx_nct_to_rows_bf16(const float* x, int64_t x_bstride, void* out, int64_t B, int64_t T, int64_t pad,
+                          int64_t C, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Attention core of nn.MultiheadAttention for short sequences (S_q, S_k <= 64; head_dim in
+ * {64, 96, 128, 192}): softmax(q k^T * scale) -> dropout -> (.) v, one CTA per (batch, head),
+ * probabilities never leave the SM (layers.py:232-234, 245-251; brain_encoder.py:165-168).
+ * q, k, v, o: rows of (B*S, row_stride) bf16 matrices, head h at columns [h*hd, (h+1)*hd) --
+ * the packed in-projection output is consumed in place.  lse: (B, H, S_q) fp32 (saved).
+ * Backward recomputes the probabilities; d_o has o's row stride.
+ * ------------------------------------------------------------------------ */
+typedef struct eegx_attn_desc {
+    int64_t B, H, Sq, Sk, hd;
+    int64_t q_rs, k_rs, v_rs, o_rs; /* row strides in elements (multiples of 8) */
+    int32_t causal;
+    float scale;
+} eegx_attn_desc;
+int eegx_attn_fwd_bf16(const eegx_attn_desc* d, const void* q, const void* k, const void* v, void* o, float* lse,
+                       const uint64_t* rng_state, uint32_t site, float p, void* stream);
+int eegx_attn_bwd_bf16(const eegx_attn_desc* d, const void* q, const void* k, const void* v, const void* o,
+                       const void* d_o, const float* lse, void* dq, void* dk, void* dv, int64_t dq_rs, int64_t dk_rs,
+                       int64_t dv_rs, const uint64_t* rng_state, uint32_t site, float p, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
