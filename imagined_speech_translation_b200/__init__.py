@@ -11,4 +11,5 @@ __version__ = "0.1.0"
 from .layers import Conv1DWithAttention, FeedForwardNetwork, SqueezeExciteBlock  # noqa: F401,E402
 from .brain_encoder import BrainRegionEncoder  # noqa: F401,E402
 from .optim import FlatAdamW  # noqa: F401,E402
-from . import distributed, ops  # noqa: F401,E402
+from .model import BARTDecoder, EEGDecodingModel  # noqa: F401,E402
+from . import distributed, fused, ops  # noqa: F401,E402

@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import nn_ops
+from . import fused, nn_ops
 from .layers import Conv1DWithAttention, _layer_norm, _mha, run_sequential
 from .nn_ops import PAD
 
@@ -83,12 +83,13 @@ class BrainRegionEncoder(nn.Module):
 
     def _fusion_layer(self, layer: nn.TransformerEncoderLayer, x):
         # norm_first: x + drop(MHA(LN1 x)); x + drop(W2 drop(gelu(W1 LN2 x)))
+        tr = layer.training
         a = _mha(layer.self_attn, _layer_norm(x, layer.norm1), None, True)
-        x = (x.float() + layer.dropout1(a.float())).to(torch.bfloat16)
+        x = fused.add_dropout(x, a, p=layer.dropout1.p, training=tr)
         h = nn_ops.linear(_layer_norm(x, layer.norm2), layer.linear1.weight, layer.linear1.bias)
-        h = layer.dropout(F.gelu(h.float())).to(torch.bfloat16)
+        h = fused.gelu_dropout(h, p=layer.dropout.p, training=tr)
         h = nn_ops.linear(h, layer.linear2.weight, layer.linear2.bias)
-        return (x.float() + layer.dropout2(h.float())).to(torch.bfloat16)
+        return fused.add_dropout(x, h, p=layer.dropout2.p, training=tr)
 
     def _region_features(self, eeg_data):
         """The four region encoders are independent until the stack: run them on four streams

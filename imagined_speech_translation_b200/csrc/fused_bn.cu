@@ -79,6 +79,15 @@ bn_stats_partial_kernel(const __nv_bfloat16* __restrict__ y, RowGeom g, int C, f
     });
 }
 
+// plain column sums of a (rows, C) bf16 matrix (bias gradients): same skeleton, every row valid
+__global__ void __launch_bounds__(CR_THREADS)
+colsum_partial_kernel(const __nv_bfloat16* __restrict__ y, RowGeom g, int C, float* __restrict__ part) {
+    col_reduce<1>(g, C, part, [&](long long m, int c, float (&acc)[1][2]) {
+        const float2 v = ld2(y + m * C + c);
+        acc[0][0] += v.x; acc[0][1] += v.y;
+    });
+}
+
 // mean / rstd from the partials (fp64), and the running-statistics update of nn.BatchNorm1d
 // (momentum; running_var takes the unbiased variance).
 __global__ void bn_stats_final_kernel(const float* __restrict__ part, int nslabs, int C, double n_valid, float eps,
@@ -524,6 +533,23 @@ int eegx_bn_stats_bf16(const void* y, int64_t B, int64_t T, int64_t pad, int64_t
     bn_stats_partial_kernel<<<grid, CR_THREADS, 0, st>>>(static_cast<const __nv_bfloat16*>(y), g, (int)C, part);
     bn_stats_final_kernel<<<(int)((C + 127) / 128), 128, 0, st>>>(part, slabs, (int)C, (double)B * (double)T, eps, mean,
                                                                   rstd, running_mean, running_var, momentum);
+    EEGX_CUDA_CHECK(cudaGetLastError());
+    return EEGX_OK;
+}
+
+int eegx_colsum_bf16(const void* y, int64_t rows, int64_t C, float* out, void* workspace, size_t workspace_bytes,
+                     void* stream) {
+    if (int rc = eegx::require_sm100()) return rc;
+    EEGX_REQUIRE(rows >= 0 && C >= 2 && (C % 2) == 0, EEGX_ERR_SHAPE, "colsum: C must be even");
+    EEGX_REQUIRE(y && out && workspace, EEGX_ERR_ARG, "colsum: NULL pointer");
+    EEGX_REQUIRE(workspace_bytes >= eegx_colreduce_workspace_bytes(C), EEGX_ERR_WORKSPACE, "colsum: workspace too small");
+    const RowGeom g{(long long)rows, 1, 0, 1};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int slabs = slabs_for(g.M, (int)C);
+    float* part = static_cast<float*>(workspace);
+    dim3 grid((unsigned)((C + CR_COLS - 1) / CR_COLS), (unsigned)slabs);
+    colsum_partial_kernel<<<grid, CR_THREADS, 0, st>>>(static_cast<const __nv_bfloat16*>(y), g, (int)C, part);
+    sum_partials_kernel<<<(int)((C + 127) / 128), 128, 0, st>>>(part, slabs, 1, (int)C, out);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
 }

@@ -93,6 +93,20 @@ def _f32(p: torch.Tensor) -> torch.Tensor:
     return p if p.dtype == torch.float32 and p.is_contiguous() else p.float().contiguous()
 
 
+def colsum(y: torch.Tensor) -> torch.Tensor:
+    """Column sums (fp32) of a (rows, C) bf16 matrix: bias gradients, fixed summation order."""
+    _need(y, "y")
+    rows, C_ = y.shape
+    out = torch.empty(C_, dtype=torch.float32, device=y.device)
+    if rows == 0:
+        return out.zero_()
+    lib = _lib.lib()
+    ws = _workspace(lib.eegx_colreduce_workspace_bytes(C_), y.device)
+    _lib.check(lib.eegx_colsum_bf16(_lib.ptr(y), rows, C_, _lib.ptr(out), _lib.ptr(ws), ws.numel(),
+                                    _lib.stream_ptr()), "eegx_colsum_bf16")
+    return out
+
+
 # ------------------------------------------------------------------------------------------ LayerNorm
 class _LayerNorm(torch.autograd.Function):
     @staticmethod

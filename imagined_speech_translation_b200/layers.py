@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import nn_ops
+from . import fused, nn_ops
 from .nn_ops import PAD
 
 
@@ -39,12 +39,14 @@ class SqueezeExciteBlock(nn.Module):
             nn.Linear(channels, channels // reduction), nn.ReLU(inplace=True),
             nn.Linear(channels // reduction, channels), nn.Sigmoid())
 
-    def forward(self, x_cl):
-        # s = mean_T(x); e = sigmoid(W2 relu(W1 s + b1) + b2); x * e   (tiny: M = B rows)
-        s = x_cl.float().mean(dim=1)
+    def forward(self, xg, B, T, p=0.0, training=True):
+        """xg: guarded channels-last rows of (B, T, C); returns dropout_p(x * e) as compact (B*T, C) rows.
+        s = mean_T(x); e = sigmoid(W2 relu(W1 s + b1) + b2)   (the two tiny Linears: M = B rows)"""
+        s = fused.group_mean(xg, B, T)
         fc1, fc2 = self.excitation[0], self.excitation[2]
-        e = torch.sigmoid(F.linear(torch.relu(F.linear(s, fc1.weight, fc1.bias)), fc2.weight, fc2.bias))
-        return x_cl * e.to(x_cl.dtype).unsqueeze(1)
+        z = torch.relu(nn_ops.linear(s.to(torch.bfloat16), fc1.weight, fc1.bias))
+        e = torch.sigmoid(nn_ops.linear(z, fc2.weight, fc2.bias).float())
+        return fused.se_scale(xg, e, B, T, p=p, training=training)
 
 
 class FeedForwardNetwork(nn.Module):
@@ -58,20 +60,31 @@ class FeedForwardNetwork(nn.Module):
         self.dropout = nn.Dropout(0.1)
 
     def forward(self, x):
-        act = F.gelu(nn_ops.linear(x, self.linear1.weight, self.linear1.bias).float())
-        gate = torch.sigmoid(nn_ops.linear(x, self.gate.weight, self.gate.bias).float())
-        h = self.dropout(act * gate).to(torch.bfloat16)
+        ag = nn_ops.linear_cat(x, self.linear1.weight, self.linear1.bias, self.gate.weight, self.gate.bias)
+        h = fused.glu(ag, p=self.dropout.p, training=self.dropout.training)
         return nn_ops.linear(h, self.linear2.weight, self.linear2.bias)
 
 
 def _mha(mod: nn.MultiheadAttention, q_in, kv_in, self_attn: bool):
     """nn.MultiheadAttention(batch_first=True) semantics (packed in_proj, q scaled by
     1/sqrt(head_dim), softmax, dropout on the probabilities in train mode, out_proj); the
-    head-averaged attention weights the reference discards are not produced."""
+    head-averaged attention weights the reference discards are not produced.  Sequences up to 64
+    tokens run the fused attention core (probabilities stay on the SM); longer ones fall back to
+    batched GEMMs with the scores in HBM."""
     B, Sq, d = q_in.shape
     H = mod.num_heads
     hd = d // H
     W, b = mod.in_proj_weight, mod.in_proj_bias
+    Sk = Sq if self_attn else kv_in.shape[1]
+    if fused.attn_supported(Sq, Sk, hd):
+        if self_attn:
+            qkv = nn_ops.linear(q_in.reshape(B * Sq, d), W, b)                   # (B*S, 3d)
+            o = fused.attn_self(qkv, B, Sq, H, p=mod.dropout, training=mod.training)
+        else:
+            q = nn_ops.linear(q_in.reshape(B * Sq, d), W[:d], b[:d])
+            kv = nn_ops.linear(kv_in.reshape(B * Sk, d), W[d:], b[d:])
+            o = fused.attn_cross(q, kv, B, Sq, Sk, H, p=mod.dropout, training=mod.training)
+        return nn_ops.linear(o, mod.out_proj.weight, mod.out_proj.bias).view(B, Sq, d)
     if self_attn:
         qkv = nn_ops.linear(q_in, W, b)                              # (B, S, 3d)
         q, k, v = qkv.split(d, dim=-1)
@@ -79,7 +92,6 @@ def _mha(mod: nn.MultiheadAttention, q_in, kv_in, self_attn: bool):
         q = nn_ops.linear(q_in, W[:d], b[:d])
         kv = nn_ops.linear(kv_in, W[d:], b[d:])
         k, v = kv.split(d, dim=-1)
-    Sk = k.shape[1]
     q = q.reshape(B, Sq, H, hd).transpose(1, 2)
     k = k.reshape(B, Sk, H, hd).transpose(1, 2)
     v = v.reshape(B, Sk, H, hd).transpose(1, 2)
@@ -92,23 +104,39 @@ def _mha(mod: nn.MultiheadAttention, q_in, kv_in, self_attn: bool):
 
 
 def _layer_norm(x, ln: nn.LayerNorm):
-    return F.layer_norm(x.float(), ln.normalized_shape, ln.weight, ln.bias, ln.eps).to(torch.bfloat16)
+    return fused.layer_norm(x, ln.weight, ln.bias, ln.eps)
 
 
 def run_sequential(seq: nn.Sequential, x):
-    """A Sequential of Linear / LayerNorm / GELU / Sigmoid / Dropout applied to bf16 rows with
-    our contractions (the containers only hold the parameters)."""
-    for m in seq:
+    """A Sequential of Linear / LayerNorm / GELU / Sigmoid / Dropout applied to bf16 rows: the
+    contractions run on the tcgen05 GEMM and the runs LayerNorm -> GELU -> Dropout / GELU -> Dropout
+    collapse into one fused kernel each (the containers only hold the parameters)."""
+    mods = list(seq)
+    i = 0
+    while i < len(mods):
+        m = mods[i]
+        nxt = mods[i + 1] if i + 1 < len(mods) else None
+        nxt2 = mods[i + 2] if i + 2 < len(mods) else None
         if isinstance(m, nn.Linear):
             x = nn_ops.linear(x, m.weight, m.bias)
+            i += 1
         elif isinstance(m, nn.LayerNorm):
-            x = _layer_norm(x, m)
+            gelu = isinstance(nxt, nn.GELU)
+            drop = nxt2 if gelu and isinstance(nxt2, nn.Dropout) else (nxt if isinstance(nxt, nn.Dropout) else None)
+            x = fused.layer_norm(x, m.weight, m.bias, m.eps, gelu=gelu, p=drop.p if drop is not None else 0.0,
+                                 training=drop.training if drop is not None else False)
+            i += 1 + int(gelu) + int(drop is not None)
         elif isinstance(m, nn.GELU):
-            x = F.gelu(x.float()).to(torch.bfloat16)
+            drop = nxt if isinstance(nxt, nn.Dropout) else None
+            x = fused.gelu_dropout(x, p=drop.p if drop is not None else 0.0,
+                                   training=drop.training if drop is not None else False)
+            i += 1 + int(drop is not None)
         elif isinstance(m, nn.Sigmoid):
             x = torch.sigmoid(x.float()).to(torch.bfloat16)
+            i += 1
         elif isinstance(m, nn.Dropout):
             x = m(x)
+            i += 1
         else:
             raise TypeError(type(m))
     return x
@@ -172,72 +200,39 @@ class Conv1DWithAttention(nn.Module):
         self.diversity_head = nn.Linear(hidden_dim, hidden_dim)
 
     # ------------------------------------------------------------------ CNN stack
-    def _batch_norm(self, y, bn: nn.BatchNorm1d, mask, n_valid):
-        """BatchNorm1d over the valid rows of a (M, C) tensor (train: biased batch variance for
-        normalisation, running_var updated with the unbiased one; eval: running statistics)."""
-        y = y.float()
-        if bn.training:
-            ym = y * mask
-            mean = ym.sum(0) / n_valid
-            var = ((y - mean) * mask).pow(2).sum(0) / n_valid
-            with torch.no_grad():
-                m = bn.momentum
-                bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
-                bn.running_var.mul_(1 - m).add_(var * (n_valid / max(n_valid - 1, 1)), alpha=m)
-                bn.num_batches_tracked += 1
-        else:
-            mean, var = bn.running_mean, bn.running_var
-        return (y - mean) * torch.rsqrt(var + bn.eps) * bn.weight + bn.bias
-
-    def _res_block(self, h, conv, bn, res, drop, B, T, mask):
-        """gelu(bn(conv(h)) + res(h)) on channels-last rows; h: (B, T, C_in) bf16."""
+    def _res_block(self, hg, conv, bn, res, drop, B, T):
+        """gelu(bn(conv(h)) + res(h)) -> dropout -> zeroed padding rows, on guarded channels-last rows
+        (reference layers.py:142-174): two GEMMs, two statistics reductions, one fused apply."""
         M = B * (T + 2 * PAD)
-        n_valid = B * T
-        buf = nn_ops.guard_pad(h)
-        y = self._batch_norm(nn_ops.conv1d_cl(buf, conv.weight, conv.bias, M), bn, mask, n_valid)
+        ya = nn_ops.conv_g(hg, conv.weight, conv.bias, M, bias_grad=not bn.training)
+        p = drop.p if drop is not None else 0.0
         if isinstance(res, nn.Identity):
-            r = buf[PAD:PAD + M].float()
-        else:
-            r = self._batch_norm(nn_ops.conv1d_cl(buf, res[0].weight, None, M), res[1], mask, n_valid)
-        out = F.gelu(y + r)
-        if drop is not None:
-            out = drop(out)
-        out = (out * mask).to(torch.bfloat16)
-        return out.view(B, T + 2 * PAD, -1)[:, PAD:PAD + T]
+            return fused.bn_act(ya, bn, hg, None, B, T, p=p, training=bn.training, drop_training=self.training)
+        yr = nn_ops.conv_g(hg, res[0].weight, None, M)
+        return fused.bn_act(ya, bn, yr, res[1], B, T, p=p, training=bn.training, drop_training=self.training)
 
-    def _depthwise_block(self, h, B, T, mask):
+    def _depthwise_block(self, hg, B, T):
         # depthwise k5 (groups = channels) -> pointwise 1x1 -> BN -> GELU   (layers.py:157-161)
-        C = h.shape[-1]
-        w = self.depthwise_conv.weight                         # (C, 1, 5)
-        xp = F.pad(h.float(), (0, 0, 2, 2))                    # (B, T+4, C) zero padded in time
-        d = self.depthwise_conv.bias.view(1, 1, C).expand(B, T, C)
-        for tap in range(5):
-            d = d + xp[:, tap:tap + T] * w[:, 0, tap].view(1, 1, C)
-        d = d.to(torch.bfloat16)
         M = B * (T + 2 * PAD)
-        buf = nn_ops.guard_pad(d)
-        pw = self.pointwise_conv
-        y = nn_ops.conv1d_cl(buf, pw.weight, pw.bias, M)
-        y = self._batch_norm(y, self.bn_depth, mask, B * T)
-        out = self.dropout_medium(F.gelu(y))
-        out = (out * mask).to(torch.bfloat16)
-        return out.view(B, T + 2 * PAD, -1)[:, PAD:PAD + T]
+        d = fused.dwconv5(hg, self.depthwise_conv.weight, self.depthwise_conv.bias, B, T)
+        pw, bn = self.pointwise_conv, self.bn_depth
+        y = nn_ops.conv_g(d, pw.weight, pw.bias, M, bias_grad=not bn.training)
+        return fused.bn_act(y, bn, None, None, B, T, p=self.dropout_medium.p, training=bn.training,
+                            drop_training=self.training)
 
     def _cnn(self, x):
         B, C, T = x.shape
         if C % 8 != 0:
             raise ValueError("n_channels must be a multiple of 8 on this path (TMA row pitch)")
-        h = x.transpose(1, 2).to(torch.bfloat16)               # channels-last
-        Tp = T + 2 * PAD
-        t = torch.arange(Tp, device=x.device)
-        mask = ((t >= PAD) & (t < PAD + T)).float().repeat(B).view(B * Tp, 1)
-        h = self._res_block(h, self.conv1, self.bn1, self.residual1, self.dropout_light, B, T, mask)
-        h = self._res_block(h, self.conv2, self.bn2, self.residual2, self.dropout_light, B, T, mask)
-        h = self._depthwise_block(h, B, T, mask)
-        h = self._res_block(h, self.conv3, self.bn3, self.residual3, self.dropout_medium, B, T, mask)
-        h = self._res_block(h, self.conv4, self.bn4, self.residual4, None, B, T, mask)
-        h = self.se_block(h)
-        return self.dropout_heavy(h)                            # (B, T, 768) bf16
+        hg = fused.to_rows(x.float())                           # guarded channels-last bf16 rows
+        hg = self._res_block(hg, self.conv1, self.bn1, self.residual1, self.dropout_light, B, T)
+        hg = self._res_block(hg, self.conv2, self.bn2, self.residual2, self.dropout_light, B, T)
+        hg = self._depthwise_block(hg, B, T)
+        hg = self._res_block(hg, self.conv3, self.bn3, self.residual3, self.dropout_medium, B, T)
+        hg = self._res_block(hg, self.conv4, self.bn4, self.residual4, None, B, T)
+        # SE re-scaling + dropout_heavy, compact (B*T, 768) rows out
+        h = self.se_block(hg, B, T, p=self.dropout_heavy.p, training=self.training)
+        return h.view(B, T, -1)
 
     # ------------------------------------------------------------------ heads
     def _mlp(self, seq: nn.Sequential, x):
@@ -269,20 +264,20 @@ class Conv1DWithAttention(nn.Module):
         pos = self.pos_emb
         if S > pos.size(1):                                     # longer than built for: tile (layers.py:222-225)
             pos = pos.repeat(1, S // pos.size(1) + 1, 1)
-        h = (h.float() + pos[:, :S]).to(torch.bfloat16)
+        h = (h + pos[:, :S]).to(torch.bfloat16)                 # bf16 + fp32 -> fp32 add, one rounding
 
         prev = None
         for i, layer in enumerate(self.attn_layers):
             a = _mha(layer['attn'], _layer_norm(h, layer['attn_norm']), None, True)
-            h = (h.float() + self.dropout_light(a.float())).to(torch.bfloat16)
+            h = fused.add_dropout(h, a, p=self.dropout_light.p, training=self.training)
             saved = h
             f = layer['ffn'](_layer_norm(h, layer['ffn_norm']))
-            h = (h.float() + self.dropout_medium(f.float())).to(torch.bfloat16)
+            h = fused.add_dropout(h, f, p=self.dropout_medium.p, training=self.training)
             if i > 0:
                 c = _mha(self.cross_scale_attn, h, prev, False)
-                h = (h.float() + 0.1 * c.float()).to(torch.bfloat16)
+                h = fused.add_dropout(h, c, scale=0.1)
             prev = saved
 
-        hf = h.float()
-        feat = (hf[:, 0] + 0.3 * hf[:, 1:4].mean(dim=1)).to(torch.bfloat16)
+        h4 = h[:, :4].float()
+        feat = (h4[:, 0] + 0.3 * h4[:, 1:4].mean(dim=1)).to(torch.bfloat16)
         return self._finish([feat, feat, feat])

@@ -12,7 +12,7 @@ from typing import Optional
 
 import torch
 
-from . import ops
+from . import fused, ops
 
 PAD = 4   # largest Conv1d padding in the encoder (kernel 9, layers.py:30)
 
@@ -88,7 +88,7 @@ class _Linear(torch.autograd.Function):
             p = pre.float()
             cdf = 0.5 * (1.0 + torch.erf(p * 0.7071067811865476))
             pdf = torch.exp(-0.5 * p * p) * 0.3989422804014327
-            dy = (dy.float() * (cdf + p * pdf)).to(torch.bfloat16)
+            dy = (dy.float() * (cdf + p * pdf)).to(torch.bfloat16).contiguous()
         w16 = _w_linear(weight)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
@@ -96,7 +96,7 @@ class _Linear(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = ops.gemm(dy, x, a_mn_major=True, b_mn_major=True, out_dtype=torch.float32)[:N]   # dy^T @ x
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dy.float().sum(0)[:N]
+            db = fused.colsum(dy)[:N]
         return dx, dw, db, None
 
 
@@ -161,7 +161,7 @@ class _ConvCL(torch.autograd.Function):
             dx = ops.gemm(a, _w_conv_dgrad(weight), b_mn_major=True)            # (M, Cin)
             dbuf = torch.nn.functional.pad(dx, (0, 0, PAD, PAD))
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dy.float().sum(0)
+            db = fused.colsum(dy)
         return dbuf, dw, db, None
 
 
@@ -169,3 +169,85 @@ def conv1d_cl(buf: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tens
     if weight.shape[1] % 8 != 0:
         raise ValueError("Conv1d in_channels must be a multiple of 8 on this path")
     return _ConvCL.apply(buf, weight, bias, M)
+
+
+class _LinearCat(torch.autograd.Function):
+    """[y1 | y2] = x [W1; W2]^T + [b1 | b2] in one GEMM (the two up-projections of the gated FFN,
+    reference layers.py:311-317, share their input): one launch forward, one dgrad, one wgrad."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        wcat = _cached(w1, "cat:" + str(id(w2)), lambda p: torch.cat([p, w2.detach()], 0).to(torch.bfloat16).contiguous())
+        bcat = torch.cat([b1.detach().float(), b2.detach().float()])
+        y = ops.gemm(x, wcat, bcat)
+        ctx.save_for_backward(x, w1, w2)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w1, w2 = ctx.saved_tensors
+        dy = dy.contiguous()
+        wcat = _cached(w1, "cat:" + str(id(w2)), lambda p: torch.cat([p, w2.detach()], 0).to(torch.bfloat16).contiguous())
+        n1 = w1.shape[0]
+        dx = ops.gemm(dy, wcat, b_mn_major=True) if ctx.needs_input_grad[0] else None
+        dw = ops.gemm(dy, x, a_mn_major=True, b_mn_major=True, out_dtype=torch.float32)
+        db = fused.colsum(dy)
+        return dx, dw[:n1], db[:n1], dw[n1:], db[n1:]
+
+
+def linear_cat(x: torch.Tensor, w1, b1, w2, b2) -> torch.Tensor:
+    """(..., K) -> (..., N1 + N2); N1, N2 multiples of 8."""
+    shp = x.shape
+    x2 = x.reshape(-1, shp[-1])
+    if x2.stride(-1) != 1 or (x2.stride(0) % 8) != 0:
+        x2 = x2.contiguous()
+    if w1.shape[0] % 8 or w2.shape[0] % 8 or shp[-1] % 8:
+        raise ValueError("linear_cat: feature sizes must be multiples of 8")
+    return _LinearCat.apply(x2, w1, b1, w2, b2).reshape(*shp[:-1], w1.shape[0] + w2.shape[0])
+
+
+class _ConvG(torch.autograd.Function):
+    """Conv1d (stride 1, 'same' zero padding k//2) on a guarded channels-last tensor
+    xg ((M + 2*PAD), Cin) -> raw output ((M + 2*PAD), Cout): rows PAD .. PAD+M are written, the rows
+    of each trial's padding zone hold don't-care values (the BatchNorm kernels skip them)."""
+
+    @staticmethod
+    def forward(ctx, xg, weight, bias, M, bias_grad):
+        Cout, Cin, k = weight.shape
+        p = k // 2
+        a = xg.as_strided((M, k * Cin), (Cin, 1), xg.storage_offset() + (PAD - p) * Cin)
+        b32 = bias.detach().float().contiguous() if bias is not None else None
+        yg = torch.empty(M + 2 * PAD, Cout, dtype=torch.bfloat16, device=xg.device)
+        ops.gemm(a, _w_conv_fwd(weight), b32, out=yg[PAD:PAD + M])
+        ctx.save_for_backward(xg, weight)
+        ctx.cfg = (M, bias is not None, bool(bias_grad))
+        return yg
+
+    @staticmethod
+    def backward(ctx, dyg):
+        xg, weight = ctx.saved_tensors
+        M, has_bias, bias_grad = ctx.cfg
+        Cout, Cin, k = weight.shape
+        p = k // 2
+        dyg = dyg.contiguous()                       # clean guarded tensor: zero outside the valid rows
+        dy = dyg[PAD:PAD + M]
+        dxg = dw = db = None
+        if ctx.needs_input_grad[1]:
+            a_view = xg.as_strided((M, k * Cin), (Cin, 1), xg.storage_offset() + (PAD - p) * Cin)
+            dwf = ops.gemm(dy, a_view, a_mn_major=True, b_mn_major=True, out_dtype=torch.float32)   # (Cout, k*Cin)
+            dw = dwf.view(Cout, k, Cin).permute(0, 2, 1)
+        if ctx.needs_input_grad[0]:
+            a = dyg.as_strided((M, k * Cout), (Cout, 1), dyg.storage_offset() + (PAD - p) * Cout)
+            dxg = torch.empty(M + 2 * PAD, Cin, dtype=torch.bfloat16, device=dyg.device)
+            ops.gemm(a, _w_conv_dgrad(weight), b_mn_major=True, out=dxg[PAD:PAD + M])
+        if has_bias and ctx.needs_input_grad[2]:
+            # a bias in front of a train-mode BatchNorm has an exactly zero gradient
+            db = fused.colsum(dy) if bias_grad else torch.zeros(Cout, dtype=torch.float32, device=dyg.device)
+        return dxg, dw, db, None, None
+
+
+def conv_g(xg: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], M: int,
+           bias_grad: bool = True) -> torch.Tensor:
+    if weight.shape[1] % 8 != 0:
+        raise ValueError("Conv1d in_channels must be a multiple of 8 on this path")
+    return _ConvG.apply(xg, weight, bias, M, bias_grad)

@@ -18,6 +18,7 @@ from typing import Optional
 import torch
 
 from . import distributed as dp
+from . import fused
 from .optim import FlatAdamW
 
 CONFIG = {
@@ -159,6 +160,8 @@ class EEGTrainer:
         return self
 
     def _eager_step(self, batch):
+        fused.begin_step()
+        fused.advance_rng(self.device)           # in-graph increment: every replay draws new dropout masks
         eeg = self._regions(batch)
         ids = batch['decoder_input_ids'].to(self.device, non_blocking=True)
         labels = batch['labels'].to(self.device, non_blocking=True)
@@ -176,14 +179,7 @@ class EEGTrainer:
                 dst.copy_(batch[k], non_blocking=True)
             self._graph.replay()
             return self._static_loss
-        eeg = self._regions(batch)
-        ids = batch['decoder_input_ids'].to(self.device, non_blocking=True)
-        labels = batch['labels'].to(self.device, non_blocking=True)
-        out = self.forward_pass(eeg, ids, labels)
-        if out.loss is None:
-            raise RuntimeError("model returned no loss")
-        (out.loss / self.config['accumulation_steps']).backward()
-        return out.loss.detach()
+        return self._eager_step(batch)
 
     def train_epoch(self, epoch):
         self.model.train()

@@ -211,6 +211,10 @@ int eegx_glu_bwd_bf16(const void* dout, const void* ag, void* dag, int64_t rows,
  * mean / rstd (C) fp32; running_mean / running_var updated in place with `momentum` (unbiased
  * variance) unless NULL.  Two fixed-order stages (bit-stable). */
 size_t eegx_colreduce_workspace_bytes(int64_t C);
+/* out[c] = sum_r y[r, c] of a (rows, C) bf16 matrix, fp32, fixed order: the bias gradients of nn.Linear /
+ * nn.Conv1d. */
+int eegx_colsum_bf16(const void* y, int64_t rows, int64_t C, float* out, void* workspace, size_t workspace_bytes,
+                     void* stream);
 int eegx_bn_stats_bf16(const void* y, int64_t B, int64_t T, int64_t pad, int64_t C, float eps, float* mean,
                        float* rstd, float* running_mean, float* running_var, float momentum, void* workspace,
                        size_t workspace_bytes, void* stream);
