@@ -199,7 +199,9 @@ def workload_config(workload, extra=None):
                            "hop=64) + full EEG-to-text train step (4 region encoders on (B, 16*129, 33), fusion, "
                            "BART decoder + LM head + CE, clip + AdamW), bf16 tensor cores / fp32 master weights, "
                            "batch 256 per GPU, data-parallel",
-               "model_params": 0, "tokens_per_trial": L_TOK, "accumulation_steps": 1, "dropout": "on (train mode)"}
+               "model_params": 0, "tokens_per_trial": L_TOK, "accumulation_steps": 1, "dropout": "on (train mode)",
+               "execution": "preprocess + forward + backward replayed as one CUDA graph; all-reduce + fused clip/AdamW "
+                            "launched after it"}
     cfg.update({"batch_per_gpu": B_PER_GPU, "channels": C, "samples": T, "n_fft": N_FFT, "hop": HOP,
                 "l2": "working set per step (>= 413 MB of trial + feature tensors) exceeds the 126 MB L2; "
                       "2 rotating input buffers"})
@@ -330,12 +332,18 @@ def run_ours(args, rank, world, local_rank):
         trainer._optimizer_step(step_scheduler=True)
         return loss
 
+    for i in range(2):
+        step(batches[i % 2])                                   # eager: builds the flat parameter / gradient buffers
+    from imagined_speech_translation_b200 import _lib as eegx_lib
+    calls0 = eegx_lib.CALLS[0]
+    trainer.capture(batches[0], warmup=0)                       # preprocess + forward + backward as one CUDA graph
+    graph_calls = eegx_lib.CALLS[0] - calls0                    # libeegx entry-point calls recorded into the graph
     for i in range(args.warmup):
         step(batches[i % 2])
     barrier()
     if sampler:
         sampler.start()
-    ops.LAUNCHES["gemm"] = 0
+    calls1 = eegx_lib.CALLS[0]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
@@ -343,7 +351,8 @@ def run_ours(args, rank, world, local_rank):
     e1.record()
     barrier()
     clocks = sampler.stop() if sampler else None
-    gemm_launches = ops.LAUNCHES["gemm"]
+    eager_calls = eegx_lib.CALLS[0] - calls1                   # optimizer entry points launched outside the graph
+    launches = graph_calls * args.steps + eager_calls
     tt = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -395,7 +404,8 @@ def run_ours(args, rank, world, local_rank):
     e2e_ms = float(te.item()) / args.steps
     h2d = 4 * B_PER_GPU * C * T + 2 * 8 * B_PER_GPU * L_TOK
 
-    # ---------------- dominant kernel: per-launch GEMM timing pass ----------------
+    # ---------------- dominant kernel: per-launch GEMM timing pass (eager, outside the graph) ----------------
+    trainer._graph = None
     ops.GEMM_TIMING = []
     step(batches[0])
     torch.cuda.synchronize()
@@ -421,10 +431,11 @@ def run_ours(args, rank, world, local_rank):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "path": "pinned host batch -> H2D (copy stream, one batch ahead) -> EEGTrainer.train_step + "
                             "optimizer step -> D2H loss"},
-            "gpu_launches": gemm_launches + args.steps * (1 + 9),
-            "gpu_launches_note": f"{gemm_launches} tcgen05 GEMM launches + per step 1 DSP kernel + 9 optimizer "
-                                 "kernels (sum-of-squares partial + final and AdamW for each of the 3 LR groups); "
-                                 "the remaining element-wise glue still runs as torch kernels",
+            "gpu_launches": launches,
+            "gpu_launches_note": f"libeegx entry-point calls (each enqueues 1-3 of our kernels): {graph_calls} per "
+                                 f"step replayed inside the CUDA graph (DSP, tcgen05 GEMMs, fused norm/activation/"
+                                 f"attention kernels) + {eager_calls // max(args.steps, 1)} per step for clip + AdamW; "
+                                 "BART decoder internals and small reshapes still run as torch kernels",
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
                          "frac": achieved / tf_peak, "traffic": None, "peak_source": src,
                          "kernel": "gemm_bf16_kernel (tcgen05)", "kernel_ms_per_step": gemm_ms,

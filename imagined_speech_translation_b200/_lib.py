@@ -120,7 +120,11 @@ def lib():
     return _lib
 
 
+CALLS = [0]   # number of libeegx compute entry-point calls (each enqueues >= 1 kernel); bench.py reads it
+
+
 def check(rc: int, what: str = "") -> None:
+    CALLS[0] += 1
     if rc != 0:
         msg = lib().eegx_last_error().decode("utf-8", "replace")
         raise EegxError(f"{what or 'libeegx'} failed with status {rc}: {msg}")

@@ -192,8 +192,10 @@ __device__ __forceinline__ void store_rows(bf16* base, long long rs, int row_lo,
     }
 }
 
+// 2*NT warps: warps [0, NT) produce dK / dV of their 16 keys (phase A), warps [NT, 2*NT) produce dQ of
+// their 16 queries (phase B), concurrently, from the same shared-memory tiles.
 template <int HD, int NT>
-__global__ void __launch_bounds__(NT * 32)
+__global__ void __launch_bounds__(2 * NT * 32)
 attn_bwd_kernel(const AttnArgs a) {
     constexpr int LD = HD + 8, ROWS = NT * 16;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -212,7 +214,7 @@ attn_bwd_kernel(const AttnArgs a) {
     for (int i = threadIdx.x; i < ROWS; i += blockDim.x) lse_s[i] = i < a.Sq ? a.lse[(long long)bh * a.Sq + i] : 0.0f;
     __syncthreads();
     // D_i = dO_i . O_i
-    for (int i = warp; i < ROWS; i += NT) {
+    for (int i = warp; i < ROWS; i += 2 * NT) {
         float acc = 0.0f;
         if (i < a.Sq && lane < HD / 8) {
             float dv[8], ov[8];
@@ -229,7 +231,7 @@ attn_bwd_kernel(const AttnArgs a) {
 
     // ---- phase A: this warp owns keys j0 .. j0+15; transposed scores S^T (rows j, columns i)
     const int j0 = warp * 16;
-    if (j0 < a.Sk) {
+    if (warp < NT && j0 < a.Sk) {
         float sT[2 * NT][4], dpT[2 * NT][4];
 #pragma unroll
         for (int nt = 0; nt < 2 * NT; ++nt)
@@ -297,8 +299,8 @@ attn_bwd_kernel(const AttnArgs a) {
     }
 
     // ---- phase B: this warp owns queries i0 .. i0+15; scores S (rows i, columns j); dQ = dS K
-    const int i0 = warp * 16;
-    if (i0 < a.Sq) {
+    const int i0 = (warp - NT) * 16;
+    if (warp >= NT && i0 < a.Sq) {
         float s[2 * NT][4], dp[2 * NT][4];
 #pragma unroll
         for (int nt = 0; nt < 2 * NT; ++nt)
@@ -357,7 +359,7 @@ int launch(const AttnArgs& a, bool backward, cudaStream_t st) {
                                  : (size_t)3 * ROWS * LD * sizeof(bf16);
     if (backward) {
         EEGX_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attn_bwd_kernel<HD, NT><<<a.B * a.H, NT * 32, smem, st>>>(a);
+        attn_bwd_kernel<HD, NT><<<a.B * a.H, 2 * NT * 32, smem, st>>>(a);
     } else {
         EEGX_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attn_fwd_kernel<HD, NT><<<a.B * a.H, NT * 32, smem, st>>>(a);

@@ -36,6 +36,7 @@ constexpr int CR_COLS = 64;
 template <int NACC, typename F>
 __device__ __forceinline__ void col_reduce(const RowGeom& g, int C, float* __restrict__ part, F f) {
     __shared__ float red[CR_THREADS / 32][NACC][CR_COLS];
+    constexpr int NW = CR_THREADS / 32;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int c = blockIdx.x * CR_COLS + 2 * lane;
     const long long rows_per = (g.M + gridDim.y - 1) / gridDim.y;
@@ -44,9 +45,18 @@ __device__ __forceinline__ void col_reduce(const RowGeom& g, int C, float* __res
     float acc[NACC][2];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k][0] = acc[k][1] = 0.0f;
-    if (c < C) {
-        for (long long m = m0 + wid; m < m1; m += CR_THREADS / 32)
-            if (g.valid(m)) f(m, c, acc);
+    if (c < C && m0 + wid < m1) {
+        // the position inside the trial is tracked incrementally (no 64-bit modulo per row)
+        long long m = m0 + wid;
+        int r = (int)(m % g.Tp);
+        const int step = NW % g.Tp;
+        const bool all_valid = g.lo == 0 && g.hi == g.Tp;
+#pragma unroll 4
+        for (; m < m1; m += NW) {
+            if (all_valid || (r >= g.lo && r < g.hi)) f(m, c, acc);
+            r += step;
+            if (r >= g.Tp) r -= g.Tp;
+        }
     }
 #pragma unroll
     for (int k = 0; k < NACC; ++k) {
@@ -59,7 +69,7 @@ __device__ __forceinline__ void col_reduce(const RowGeom& g, int C, float* __res
         if (blockIdx.x * CR_COLS + cc < C) {
             float t = 0.0f;
 #pragma unroll
-            for (int w = 0; w < CR_THREADS / 32; ++w) t += red[w][k][cc];
+            for (int w = 0; w < NW; ++w) t += red[w][k][cc];
             part[((long long)blockIdx.y * NACC + k) * C + blockIdx.x * CR_COLS + cc] = t;
         }
     }

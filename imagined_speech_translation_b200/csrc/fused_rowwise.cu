@@ -162,15 +162,24 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
     }
 }
 
-// out[j][c] = sum_b part[b][j][c], fixed order (bit-stable)
-__global__ void colsum_partials_kernel(const float* __restrict__ part, int nblocks, int nvec, int C,
-                                       float* __restrict__ out0, float* __restrict__ out1) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    for (int j = 0; j < nvec; ++j) {
-        float t = 0.0f;
-        for (int b = 0; b < nblocks; ++b) t += part[((long long)b * nvec + j) * C + c];
-        (j == 0 ? out0 : out1)[c] = t;
+// out_j[c] = sum_b part[b][j][c] in a fixed order (bit-stable): a CTA owns 32 columns, its 8 warps
+// each sum every 8th block (coalesced 128-byte rows), then the warps are added in order.
+__global__ void __launch_bounds__(256)
+colsum_partials_kernel(const float* __restrict__ part, int nblocks, int nvec, int C,
+                       float* __restrict__ out0, float* __restrict__ out1) {
+    __shared__ float red[8][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane, j = blockIdx.y;
+    float t = 0.0f;
+    if (c < C)
+        for (int b = wid; b < nblocks; b += 8) t += part[((long long)b * nvec + j) * C + c];
+    red[wid][lane] = t;
+    __syncthreads();
+    if (wid == 0 && c < C) {
+        float r = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) r += red[w][lane];
+        (j == 0 ? out0 : out1)[c] = r;
     }
 }
 
@@ -373,7 +382,7 @@ int eegx_layernorm_bwd_bf16(const void* dy, const void* x, const float* gamma, c
         case 5: case 6: launch_ln_bwd<6>(dy, x, gamma, beta, mean, rstd, dx, part, grid, rows, (int)C, act, dc, st); break;
         default: launch_ln_bwd<8>(dy, x, gamma, beta, mean, rstd, dx, part, grid, rows, (int)C, act, dc, st); break;
     }
-    colsum_partials_kernel<<<(int)((C + 127) / 128), 128, 0, st>>>(part, grid, 2, (int)C, dgamma, dbeta);
+    colsum_partials_kernel<<<dim3((unsigned)((C + 31) / 32), 2), 256, 0, st>>>(part, grid, 2, (int)C, dgamma, dbeta);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
 }

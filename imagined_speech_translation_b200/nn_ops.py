@@ -55,6 +55,27 @@ def _w_conv_dgrad(w):        # (Cout, Cin, k) -> (k*Cout, Cin) bf16 with taps fl
     return _cached(w, "convd", lambda p: p.flip(2).permute(2, 0, 1).reshape(-1, p.shape[1]).to(torch.bfloat16).contiguous())
 
 
+
+def _wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """dW (N, K) fp32 = dy^T x, reduction over the R rows.  The output is small (N x K) while R is
+    ~10^4, so a plain launch fills only N*K / (128*256) of the 148 SMs: split the reduction into s
+    row-chunks run as GEMM batches (s * tiles ~ one wave) and add the partials in a fixed order."""
+    R, N = dy.shape
+    K = x.shape[1]
+    bn = 64 if K <= 64 else (256 if K > 128 and (K % 256 == 0 or K >= 1024) else 128)
+    tiles = -(-N // 128) * -(-K // bn)
+    s = 1
+    while tiles * s * 2 <= 160 and R % (s * 2) == 0 and (R // (s * 2)) % 8 == 0 and R // (s * 2) >= 512:
+        s *= 2
+    if s == 1:
+        return ops.gemm(dy, x, a_mn_major=True, b_mn_major=True, out_dtype=torch.float32)
+    chunk = R // s
+    dy3 = dy.as_strided((s, chunk, N), (chunk * dy.stride(0), dy.stride(0), 1), dy.storage_offset())
+    x3 = x.as_strided((s, chunk, K), (chunk * x.stride(0), x.stride(0), 1), x.storage_offset())
+    part = ops.gemm(dy3, x3, a_mn_major=True, b_mn_major=True, out_dtype=torch.float32)      # (s, N, K)
+    return part.sum(0)
+
+
 class _Linear(torch.autograd.Function):
     """y = x W^T + b (optionally GELU) on (M, K) bf16 rows; dW returned in fp32 for the master weight."""
 
@@ -94,7 +115,7 @@ class _Linear(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = ops.gemm(dy, w16, b_mn_major=True)                                   # (M,N) @ (N,K)
         if ctx.needs_input_grad[1]:
-            dw = ops.gemm(dy, x, a_mn_major=True, b_mn_major=True, out_dtype=torch.float32)[:N]   # dy^T @ x
+            dw = _wgrad(dy, x)[:N]                                                       # dy^T @ x
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = fused.colsum(dy)[:N]
         return dx, dw, db, None
@@ -152,7 +173,7 @@ class _ConvCL(torch.autograd.Function):
         dbuf = dw = db = None
         if ctx.needs_input_grad[1]:
             a_view = buf.as_strided((M, k * Cin), (Cin, 1), buf.storage_offset() + (PAD - p) * Cin)
-            dwf = ops.gemm(dy, a_view, a_mn_major=True, b_mn_major=True, out_dtype=torch.float32)  # (Cout, k*Cin)
+            dwf = _wgrad(dy, a_view)                                                     # (Cout, k*Cin)
             dw = dwf.view(Cout, k, Cin).permute(0, 2, 1).contiguous()
         if ctx.needs_input_grad[0]:
             # dx = conv of the (guarded) dy with the flipped taps: rows overlap again
@@ -190,7 +211,7 @@ class _LinearCat(torch.autograd.Function):
         wcat = _cached(w1, "cat:" + str(id(w2)), lambda p: torch.cat([p, w2.detach()], 0).to(torch.bfloat16).contiguous())
         n1 = w1.shape[0]
         dx = ops.gemm(dy, wcat, b_mn_major=True) if ctx.needs_input_grad[0] else None
-        dw = ops.gemm(dy, x, a_mn_major=True, b_mn_major=True, out_dtype=torch.float32)
+        dw = _wgrad(dy, x)
         db = fused.colsum(dy)
         return dx, dw[:n1], db[:n1], dw[n1:], db[n1:]
 
@@ -234,7 +255,7 @@ class _ConvG(torch.autograd.Function):
         dxg = dw = db = None
         if ctx.needs_input_grad[1]:
             a_view = xg.as_strided((M, k * Cin), (Cin, 1), xg.storage_offset() + (PAD - p) * Cin)
-            dwf = ops.gemm(dy, a_view, a_mn_major=True, b_mn_major=True, out_dtype=torch.float32)   # (Cout, k*Cin)
+            dwf = _wgrad(dy, a_view)                                                     # (Cout, k*Cin)
             dw = dwf.view(Cout, k, Cin).permute(0, 2, 1)
         if ctx.needs_input_grad[0]:
             a = dyg.as_strided((M, k * Cout), (Cout, 1), dyg.storage_offset() + (PAD - p) * Cout)
