@@ -94,6 +94,8 @@ SIGNATURES.update({
     "eegx_se_scale_fwd_bf16": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64] + _RNG + [_P]),
     "eegx_se_scale_bwd_bf16": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64] + _RNG + [_P]),
     "eegx_nct_to_rows_bf16": (_I, [_P, _I64, _P, _I64, _I64, _I64, _I64, _P]),
+    "eegx_ce_fwd_bf16": (_I, [_P, _I64, _P, _I64, _I64, _I64, _P, _P, _P]),
+    "eegx_ce_bwd_bf16": (_I, [_P, _I64, _P, _P, _P, _P, _I64, _I64, _I64, _P]),
     "eegx_attn_fwd_bf16": (_I, [C.POINTER(AttnDesc), _P, _P, _P, _P, _P] + _RNG + [_P]),
     "eegx_attn_bwd_bf16": (_I, [C.POINTER(AttnDesc)] + [_P] * 9 + [_I64, _I64, _I64] + _RNG + [_P]),
 })

@@ -12,6 +12,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from . import fused, nn_ops
 from .brain_encoder import BrainRegionEncoder
 from .layers import run_sequential
 
@@ -39,6 +40,8 @@ class BARTDecoder(nn.Module):
         self.bart_dim = self.bart.config.d_model
         self.eeg_to_bart = nn.Sequential(nn.Linear(hidden_dim, self.bart_dim), nn.LayerNorm(self.bart_dim))
         self.autocast_dtype = autocast_dtype
+        act = self.bart.config.activation_function
+        self.fused_decoder = act == "gelu"          # our decoder path implements exact GELU only
 
     def create_encoder_sequence(self, eeg_feat):
         B = eeg_feat.shape[0]
@@ -47,12 +50,70 @@ class BARTDecoder(nn.Module):
         return proj.unsqueeze(1).expand(-1, n, -1), torch.ones(B, n, device=eeg_feat.device)
 
     def forward(self, eeg_feat, decoder_input_ids=None, labels=None, **kwargs):
+        """Teacher-forced loss.  With decoder_input_ids and labels given (the train step,
+        trainer.py:40-67) the decoder runs on our kernels (``fused_decoder``); every other call
+        signature goes through the stock ``transformers`` forward."""
+        if (self.fused_decoder and decoder_input_ids is not None and labels is not None and not kwargs
+                and eeg_feat.is_cuda and decoder_input_ids.shape[1] <= fused.ATTN_MAX_S):
+            return self._forward_fused(eeg_feat, decoder_input_ids, labels)
         from transformers.modeling_outputs import BaseModelOutput
         enc, mask = self.create_encoder_sequence(eeg_feat)
         with torch.autocast("cuda", dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):
             return self.bart(input_ids=None, attention_mask=mask,
                              encoder_outputs=BaseModelOutput(last_hidden_state=enc),
-                             decoder_input_ids=decoder_input_ids, labels=labels, return_dict=True)
+                             decoder_input_ids=decoder_input_ids, labels=labels, return_dict=True, **kwargs)
+
+    # ------------------------------------------------------------------ fused decoder (SURVEY.md 8(f) row f1)
+    def _attn_block(self, attn, h, kv_src, B, Sq, Sk, causal, p_attn, training):
+        """BartAttention (modeling_bart.py:143-258): q/k/v projections, softmax(q k^T / sqrt(hd)) v, out_proj."""
+        H = attn.num_heads
+        if kv_src is None:
+            qkv = nn_ops.linear_cat(h, attn.q_proj.weight, attn.q_proj.bias, attn.k_proj.weight, attn.k_proj.bias,
+                                    attn.v_proj.weight, attn.v_proj.bias)
+            o = fused.attn_self(qkv, B, Sq, H, p=p_attn, training=training, causal=causal)
+        else:
+            q = nn_ops.linear(h, attn.q_proj.weight, attn.q_proj.bias)
+            kv = nn_ops.linear_cat(kv_src, attn.k_proj.weight, attn.k_proj.bias, attn.v_proj.weight, attn.v_proj.bias)
+            o = fused.attn_cross(q, kv, B, Sq, Sk, H, p=p_attn, training=training)
+        return nn_ops.linear(o, attn.out_proj.weight, attn.out_proj.bias)
+
+    def _forward_fused(self, eeg_feat, decoder_input_ids, labels):
+        """BartDecoder + lm_head + CrossEntropyLoss of transformers' BartForConditionalGeneration
+        (modeling_bart.py:553-680, 836-960) for the teacher-forced case: post-LN decoder layers with
+        causal self-attention, cross-attention over the 6-vector EEG memory, GELU FFN; bf16 activations
+        on the tcgen05 GEMM and the fused kernels, the loss through the fused LM-head cross-entropy."""
+        from transformers.modeling_outputs import Seq2SeqLMOutput
+        bart = self.bart
+        dec = bart.model.decoder
+        cfg = bart.config
+        tr = dec.training
+        B, L = decoder_input_ids.shape
+        d = cfg.d_model
+        n_mem = cfg.encoder_layers
+        proj = run_sequential(self.eeg_to_bart, eeg_feat.to(torch.bfloat16))                 # (B, d) bf16
+        mem = proj.unsqueeze(1).expand(B, n_mem, d).reshape(B * n_mem, d)                    # repeated 6x (bart_decoder.py:29-33)
+
+        emb = dec.embed_tokens(decoder_input_ids)                                            # includes embed_scale
+        pos = dec.embed_positions.weight[dec.embed_positions.offset:dec.embed_positions.offset + L]
+        h = (emb + pos.unsqueeze(0)).to(torch.bfloat16).reshape(B * L, d)
+        ln = dec.layernorm_embedding
+        h = fused.layer_norm(h, ln.weight, ln.bias, ln.eps, p=dec.dropout, training=tr)
+        for layer in dec.layers:
+            p = layer.dropout
+            a = self._attn_block(layer.self_attn, h, None, B, L, L, True, layer.self_attn.dropout, tr)
+            ln = layer.self_attn_layer_norm
+            h = fused.layer_norm(fused.add_dropout(h, a, p=p, training=tr), ln.weight, ln.bias, ln.eps)
+            a = self._attn_block(layer.encoder_attn, h, mem, B, L, n_mem, False, layer.encoder_attn.dropout, tr)
+            ln = layer.encoder_attn_layer_norm
+            h = fused.layer_norm(fused.add_dropout(h, a, p=p, training=tr), ln.weight, ln.bias, ln.eps)
+            f = nn_ops.linear(h, layer.fc1.weight, layer.fc1.bias)
+            f = fused.gelu_dropout(f, p=layer.activation_dropout, training=tr)
+            f = nn_ops.linear(f, layer.fc2.weight, layer.fc2.bias)
+            ln = layer.final_layer_norm
+            h = fused.layer_norm(fused.add_dropout(h, f, p=p, training=tr), ln.weight, ln.bias, ln.eps)
+        loss, logits = nn_ops.lm_head_cross_entropy(h, bart.lm_head.weight, bart.final_logits_bias.reshape(-1),
+                                                    labels.reshape(-1))
+        return Seq2SeqLMOutput(loss=loss, logits=logits.view(B, L, -1))
 
     def generate_from_eeg(self, eeg_feat, max_length=32, **kwargs):
         from transformers.modeling_outputs import BaseModelOutput

@@ -192,39 +192,99 @@ def conv1d_cl(buf: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tens
     return _ConvCL.apply(buf, weight, bias, M)
 
 
+def _w_cat(ws):
+    """bf16 pack of several (N_i, K) weights stacked along N (cached on the first weight's version)."""
+    tag = "cat:" + ",".join(str(id(w)) for w in ws[1:])
+    return _cached(ws[0], tag, lambda p: torch.cat([p] + [w.detach() for w in ws[1:]], 0).to(torch.bfloat16).contiguous())
+
+
 class _LinearCat(torch.autograd.Function):
-    """[y1 | y2] = x [W1; W2]^T + [b1 | b2] in one GEMM (the two up-projections of the gated FFN,
-    reference layers.py:311-317, share their input): one launch forward, one dgrad, one wgrad."""
+    """[y1 | y2 | ...] = x [W1; W2; ...]^T + [b1 | b2 | ...] in one GEMM: projections that share their
+    input (the two up-projections of the gated FFN, reference layers.py:311-317; q/k/v projections) cost
+    one launch forward, one dgrad and one wgrad."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2):
-        wcat = _cached(w1, "cat:" + str(id(w2)), lambda p: torch.cat([p, w2.detach()], 0).to(torch.bfloat16).contiguous())
-        bcat = torch.cat([b1.detach().float(), b2.detach().float()])
-        y = ops.gemm(x, wcat, bcat)
-        ctx.save_for_backward(x, w1, w2)
+    def forward(ctx, x, *wb):
+        n = len(wb) // 2
+        ws, bs = wb[:n], wb[n:]
+        bcat = torch.cat([b.detach().float() for b in bs])
+        y = ops.gemm(x, _w_cat(ws), bcat)
+        ctx.save_for_backward(x, *ws)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, w1, w2 = ctx.saved_tensors
+        x, *ws = ctx.saved_tensors
         dy = dy.contiguous()
-        wcat = _cached(w1, "cat:" + str(id(w2)), lambda p: torch.cat([p, w2.detach()], 0).to(torch.bfloat16).contiguous())
-        n1 = w1.shape[0]
-        dx = ops.gemm(dy, wcat, b_mn_major=True) if ctx.needs_input_grad[0] else None
+        dx = ops.gemm(dy, _w_cat(ws), b_mn_major=True) if ctx.needs_input_grad[0] else None
         dw = _wgrad(dy, x)
         db = fused.colsum(dy)
-        return dx, dw[:n1], db[:n1], dw[n1:], db[n1:]
+        sizes = [w.shape[0] for w in ws]
+        return (dx, *dw.split(sizes, 0), *db.split(sizes, 0))
 
 
-def linear_cat(x: torch.Tensor, w1, b1, w2, b2) -> torch.Tensor:
-    """(..., K) -> (..., N1 + N2); N1, N2 multiples of 8."""
+def linear_cat(x: torch.Tensor, *wb) -> torch.Tensor:
+    """linear_cat(x, w1, b1, w2, b2, ...): (..., K) -> (..., N1 + N2 + ...); all N_i multiples of 8."""
+    ws, bs = wb[0::2], wb[1::2]
     shp = x.shape
     x2 = x.reshape(-1, shp[-1])
     if x2.stride(-1) != 1 or (x2.stride(0) % 8) != 0:
         x2 = x2.contiguous()
-    if w1.shape[0] % 8 or w2.shape[0] % 8 or shp[-1] % 8:
+    if any(w.shape[0] % 8 for w in ws) or shp[-1] % 8:
         raise ValueError("linear_cat: feature sizes must be multiples of 8")
-    return _LinearCat.apply(x2, w1, b1, w2, b2).reshape(*shp[:-1], w1.shape[0] + w2.shape[0])
+    return _LinearCat.apply(x2, *ws, *bs).reshape(*shp[:-1], sum(w.shape[0] for w in ws))
+
+
+class _LMHeadCE(torch.autograd.Function):
+    """mean cross-entropy of (h W^T + bias) against labels (ignore_index = -100) without fp32 logits:
+    bf16 logits from the GEMM, one-pass CE forward, in-kernel (softmax - onehot) backward, then the
+    dgrad / wgrad GEMMs.  Returns (loss, logits (rows, V) bf16 view)."""
+
+    @staticmethod
+    def forward(ctx, h, weight, bias, labels):
+        import ctypes as C
+        from . import _lib
+        rows, V = h.shape[0], weight.shape[0]
+        w16 = _w_linear(weight)                                  # rows padded to a multiple of 8
+        ld = w16.shape[0]
+        b32 = torch.zeros(ld, dtype=torch.float32, device=h.device)
+        if bias is not None:
+            b32[:V] = bias.detach().float().reshape(-1)
+        logits = ops.gemm(h, w16, b32)                           # (rows, ld) bf16
+        labels = labels.reshape(-1).contiguous()
+        loss_rows = torch.empty(rows, dtype=torch.float32, device=h.device)
+        lse = torch.empty_like(loss_rows)
+        _lib.check(_lib.lib().eegx_ce_fwd_bf16(_lib.ptr(logits), ld, _lib.ptr(labels), rows, V, -100,
+                                               _lib.ptr(loss_rows), _lib.ptr(lse), _lib.stream_ptr()),
+                   "eegx_ce_fwd_bf16")
+        n_valid = (labels != -100).sum().float()
+        loss = loss_rows.sum() / n_valid
+        ctx.save_for_backward(h, weight, logits, labels, lse, n_valid)
+        ctx.mark_non_differentiable(logits)
+        return loss, logits
+
+    @staticmethod
+    def backward(ctx, dloss, _dlogits):
+        from . import _lib
+        h, weight, logits, labels, lse, n_valid = ctx.saved_tensors
+        rows, V, ld = h.shape[0], weight.shape[0], logits.shape[1]
+        coef = (dloss.float() / n_valid).reshape(1).contiguous()
+        dlogits = torch.empty_like(logits)
+        _lib.check(_lib.lib().eegx_ce_bwd_bf16(_lib.ptr(logits), ld, _lib.ptr(labels), _lib.ptr(lse), _lib.ptr(coef),
+                                               _lib.ptr(dlogits), rows, V, -100, _lib.stream_ptr()),
+                   "eegx_ce_bwd_bf16")
+        w16 = _w_linear(weight)
+        dh = ops.gemm(dlogits, w16, b_mn_major=True) if ctx.needs_input_grad[0] else None
+        dw = _wgrad(dlogits, h)[:V] if ctx.needs_input_grad[1] else None
+        return dh, dw, None, None
+
+
+def lm_head_cross_entropy(h: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor],
+                          labels: torch.Tensor):
+    """h: (rows, K) bf16; weight: (V, K); bias: (V,) or None; labels: (rows,) int64 with -100 = ignore.
+    Returns (mean loss over the non-ignored rows, logits (rows, V) bf16)."""
+    loss, logits = _LMHeadCE.apply(h.contiguous(), weight, bias, labels)
+    return loss, logits[:, :weight.shape[0]]
 
 
 class _ConvG(torch.autograd.Function):

@@ -274,6 +274,20 @@ int eegx_attn_bwd_bf16(const eegx_attn_desc* d, const void* q, const void* k, co
                        const void* d_o, const float* lse, void* dq, void* dk, void* dv, int64_t dq_rs, int64_t dk_rs,
                        int64_t dv_rs, const uint64_t* rng_state, uint32_t site, float p, void* stream);
 
+
+/* ------------------------------------------------------------------------
+ * Cross-entropy at the loss end of the train step (main_model/src/models/bart_decoder.py:41-48 ->
+ * BartForConditionalGeneration: lm_head + final_logits_bias + CrossEntropyLoss(ignore_index)).
+ * logits: (rows, ld) bf16 with V <= ld valid columns (the LM-head GEMM output, bias fused).
+ *   fwd: lse[r] = logsumexp(logits[r, :V]); loss_rows[r] = lse[r] - logits[r, labels[r]] (0 if ignored)
+ *   bwd: dlogits[r, v] = (exp(logits[r, v] - lse[r]) - [v == labels[r]]) * coef[0]  (0 on ignored rows and
+ *        on the padding columns [V, ld)); coef: device scalar = dloss / n_valid.
+ * ------------------------------------------------------------------------ */
+int eegx_ce_fwd_bf16(const void* logits, int64_t ld, const int64_t* labels, int64_t rows, int64_t V,
+                     int64_t ignore_index, float* loss_rows, float* lse, void* stream);
+int eegx_ce_bwd_bf16(const void* logits, int64_t ld, const int64_t* labels, const float* lse, const float* coef,
+                     void* dlogits, int64_t rows, int64_t V, int64_t ignore_index, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
