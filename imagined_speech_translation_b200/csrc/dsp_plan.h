@@ -39,6 +39,7 @@ size_t dsp_generic_smem_bytes(int T, int n_fft, int hop, int numtaps);
 // Tuned kernel for n_fft = 256, hop = 64, 65 taps (BASELINE config 2).
 bool dsp_tuned_supported(const eegx_dsp_plan* plan);
 int launch_dsp_tuned(const eegx_dsp_plan* plan, const DspArgs& a, cudaStream_t st);
+int launch_dsp_pair(const eegx_dsp_plan* plan, const DspArgs& a, cudaStream_t st);
 int dsp_tuned_table_floats();
 void dsp_tuned_fill_tables(float* host);
 

@@ -474,6 +474,7 @@ int launch_dsp_tuned(const eegx_dsp_plan* plan, const DspArgs& d, cudaStream_t s
     a.z_eps = plan->z_eps;
     for (int i = 0; i < 65; ++i) a.taps_rev[i] = plan->h_taps[64 - i];
     switch (plan->tuned_variant) {
+        case 3: return launch_dsp_pair(plan, d, st);    // packed f32x2, 2 rows per tile (dsp_tuned2.cu)
         case 1: return launch_variant<1, 96>(a, st);    // 4 CTAs/SM x 3 warps, 1 row per tile
         case 2: return launch_variant<2, 192>(a, st);   // 2 CTAs/SM x 6 warps, 2 rows per tile
         default: return launch_variant<1, 96>(a, st);

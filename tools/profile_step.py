@@ -18,6 +18,8 @@ opt = tr.build_optimizer(model, cfg)
 sched = tr.cosine_schedule_with_warmup(opt, 2, 1000)
 t = tr.EEGTrainer(model, None, None, None, opt, sched, cfg, front_end=fe, region_channel_counts=counts)
 model.train()
+if os.environ.get('EEGX_SERIAL', '0') == '1':
+    model.brain_encoder.parallel_regions = False
 g = torch.Generator(device="cuda").manual_seed(1)
 raw = 20 * torch.randn(B, C, T, device="cuda", generator=g)
 labels = torch.randint(1, 51271, (B, 16), device="cuda", generator=g); labels[:, 12:] = -100
@@ -46,7 +48,7 @@ print(f"B={B}: {ms:.2f} ms/step  {B/ms*1e3:.0f} trials/s  loss {loss.item():.3f}
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     step(); torch.cuda.synchronize()
-tab = prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=70)
+tab = prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=200)
 os.makedirs("gpurun_out", exist_ok=True)
 open(os.path.join("gpurun_out", f"step_profile_B{B}.txt"), "w").write(tab)
-print(tab[:6000])
+print(tab[:3000])

@@ -91,6 +91,105 @@ __global__ void k_lds128(float* out) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc.x + acc.y + acc.z + acc.w;
 }
 
+
+__global__ void k_fadd(float* out, float a) {
+    float acc[ACC];
+#pragma unroll
+    for (int i = 0; i < ACC; ++i) acc[i] = threadIdx.x * 1e-3f + i;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < ACC; ++i) asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(acc[i]) : "f"(a));
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < ACC; ++i) s += acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// 1 FFMA : 1 FADD interleaved on independent accumulators (do they share a pipe?)
+__global__ void k_mix_ffma_fadd(float* out, float a, float b) {
+    float acc[ACC], acd[ACC];
+#pragma unroll
+    for (int i = 0; i < ACC; ++i) { acc[i] = threadIdx.x * 1e-3f + i; acd[i] = i; }
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < ACC; ++i) {
+            asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(acc[i]) : "f"(a), "f"(b));
+            asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(acd[i]) : "f"(b));
+        }
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < ACC; ++i) s += acc[i] + acd[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// 2 FFMA : 1 DFMA interleaved (is the fp64 pipe usable as extra FMA capacity?)
+__global__ void k_mix_ffma_dfma(float* out, float a, float b, double c) {
+    float acc[ACC];
+    double dcc[ACC / 2];
+#pragma unroll
+    for (int i = 0; i < ACC; ++i) acc[i] = threadIdx.x * 1e-3f + i;
+#pragma unroll
+    for (int i = 0; i < ACC / 2; ++i) dcc[i] = i;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < ACC; ++i) {
+            asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(acc[i]) : "f"(a), "f"(b));
+            if ((i & 1) == 0) asm volatile("fma.rn.f64 %0, %0, %1, %1;" : "+d"(dcc[i / 2]) : "d"(c));
+        }
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < ACC; ++i) s += acc[i];
+#pragma unroll
+    for (int i = 0; i < ACC / 2; ++i) s += (float)dcc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void k_dfma(float* out, double c) {
+    double dcc[ACC];
+#pragma unroll
+    for (int i = 0; i < ACC; ++i) dcc[i] = i + threadIdx.x;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < ACC; ++i) asm volatile("fma.rn.f64 %0, %0, %1, %1;" : "+d"(dcc[i]) : "d"(c));
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < ACC; ++i) s += (float)dcc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// FFMA2 with both multiplicands in registers + 1 LDS.64 per 4 FFMA2 (constant pairs fetched from smem)
+__global__ void k_ffma2_lds(float* out, float a) {
+    __shared__ unsigned long long tab[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        unsigned long long v; float f = 1.0f + i * 1e-6f;
+        asm volatile("mov.b64 %0, {%1, %1};" : "=l"(v) : "f"(f));
+        tab[i] = v;
+    }
+    __syncthreads();
+    unsigned long long acc[ACC], bv;
+    asm volatile("mov.b64 %0, {%1, %1};" : "=l"(bv) : "f"(a));
+#pragma unroll
+    for (int i = 0; i < ACC; ++i) { float x = threadIdx.x * 1e-3f + i; asm volatile("mov.b64 %0, {%1, %1};" : "=l"(acc[i]) : "f"(x)); }
+    int idx = threadIdx.x & 7;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < ACC; i += 4) {
+            const unsigned long long w = tab[(idx + i) & 255];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc[i + j]) : "l"(w), "l"(bv));
+        }
+        idx += 3;
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < ACC; ++i) { float lo, hi; asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[i])); s += lo + hi; }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <typename F>
 float time_ms(F f) {
     cudaEvent_t a, b;
@@ -122,6 +221,16 @@ int main() {
     printf("LG2  : %.3f ms  %.2f Tops/s   (%.1f /clk/SM)\n", t3, lanes / t3 * 1e-9, lanes / (t3 * 1e-3) / sms / (clk * 1e3));
     printf("SHFL : %.3f ms  %.2f Tlane/s  (%.1f lanes/clk/SM)\n", t4, lanes / t4 * 1e-9, lanes / (t4 * 1e-3) / sms / (clk * 1e3));
     printf("LDS128: %.3f ms %.2f TB/s     (%.1f B/clk/SM)\n", t5, 16 * lanes / t5 * 1e-9, 16 * lanes / (t5 * 1e-3) / sms / (clk * 1e3));
+    float t6 = time_ms([&] { k_fadd<<<blocks, threads>>>(out, 0.5f); });
+    float t7 = time_ms([&] { k_mix_ffma_fadd<<<blocks, threads>>>(out, 1.0001f, 0.5f); });
+    float t8 = time_ms([&] { k_dfma<<<blocks, threads>>>(out, 1.0000001); });
+    float t9 = time_ms([&] { k_mix_ffma_dfma<<<blocks, threads>>>(out, 1.0001f, 0.5f, 1.0000001); });
+    float t10 = time_ms([&] { k_ffma2_lds<<<blocks, threads>>>(out, 0.5f); });
+    printf("FADD : %.3f ms  (%.1f add/clk/SM)\n", t6, lanes / (t6 * 1e-3) / sms / (clk * 1e3));
+    printf("FFMA+FADD 1:1: %.3f ms  (%.1f fp-ops/clk/SM; 2 ops per pair)\n", t7, 2 * lanes / (t7 * 1e-3) / sms / (clk * 1e3));
+    printf("DFMA : %.3f ms  (%.1f dfma/clk/SM)\n", t8, lanes / (t8 * 1e-3) / sms / (clk * 1e3));
+    printf("FFMA+DFMA 2:1: %.3f ms  (%.1f ffma/clk/SM + %.1f dfma/clk/SM)\n", t9, lanes / (t9 * 1e-3) / sms / (clk * 1e3), 0.5 * lanes / (t9 * 1e-3) / sms / (clk * 1e3));
+    printf("FFMA2 + LDS.64 per 4: %.3f ms  (%.1f fma/clk/SM)\n", t10, 2 * lanes / (t10 * 1e-3) / sms / (clk * 1e3));
     cudaError_t e = cudaGetLastError();
     printf("status: %s\n", cudaGetErrorString(e));
     return e != cudaSuccess;
