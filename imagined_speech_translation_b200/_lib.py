@@ -75,7 +75,7 @@ _RNG = [_P, _U32, _F]            # rng_state, site, p
 SIGNATURES.update({
     "eegx_layernorm_fwd_bf16": (_I, [_P, _P, _P, _P, _P, _P, _I64, _I64, _F, _I] + _RNG + [_P]),
     "eegx_layernorm_bwd_workspace_bytes": (_SZ, [_I64]),
-    "eegx_layernorm_bwd_bf16": (_I, [_P] * 9 + [_P, _SZ, _I64, _I64, _I] + _RNG + [_P]),
+    "eegx_layernorm_bwd_bf16": (_I, [_P] * 9 + [_I, _P, _SZ, _I64, _I64, _I] + _RNG + [_P]),
     "eegx_add_dropout_fwd_bf16": (_I, [_P, _P, _P, _I64, _F] + _RNG + [_P]),
     "eegx_dropout_scale_bf16": (_I, [_P, _P, _I64, _F] + _RNG + [_P]),
     "eegx_gelu_dropout_fwd_bf16": (_I, [_P, _P, _I64] + _RNG + [_P]),
@@ -83,7 +83,8 @@ SIGNATURES.update({
     "eegx_glu_fwd_bf16": (_I, [_P, _P, _I64, _I64] + _RNG + [_P]),
     "eegx_glu_bwd_bf16": (_I, [_P, _P, _P, _I64, _I64] + _RNG + [_P]),
     "eegx_colreduce_workspace_bytes": (_SZ, [_I64]),
-    "eegx_colsum_bf16": (_I, [_P, _I64, _I64, _P, _P, _SZ, _P]),
+    "eegx_colsum_bf16": (_I, [_P, _I64, _I64, _I64, _P, _I, _P, _SZ, _P]),
+    "eegx_accumulate_partials_f32": (_I, [_P, _I64, _I64, _P, _I, _P]),
     "eegx_bn_stats_bf16": (_I, [_P, _I64, _I64, _I64, _I64, _F, _P, _P, _P, _P, _F, _P, _SZ, _P]),
     "eegx_bn_act_fwd_bf16": (_I, [_P] * 10 + [_I, _P, _I64, _I64, _I64, _I64] + _RNG + [_P]),
     "eegx_bn_act_bwd_bf16": (_I, [_P] * 11 + [_I, _I, _P, _P, _P, _P, _SZ, _I64, _I64, _I64, _I64] + _RNG + [_P]),

@@ -195,7 +195,7 @@ __device__ __forceinline__ void store_rows(bf16* base, long long rs, int row_lo,
 // 2*NT warps: warps [0, NT) produce dK / dV of their 16 keys (phase A), warps [NT, 2*NT) produce dQ of
 // their 16 queries (phase B), concurrently, from the same shared-memory tiles.
 template <int HD, int NT>
-__global__ void __launch_bounds__(2 * NT * 32)
+__global__ void __launch_bounds__(2 * NT * 32, 2)
 attn_bwd_kernel(const AttnArgs a) {
     constexpr int LD = HD + 8, ROWS = NT * 16;
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -91,9 +91,9 @@ bn_stats_partial_kernel(const __nv_bfloat16* __restrict__ y, RowGeom g, int C, f
 
 // plain column sums of a (rows, C) bf16 matrix (bias gradients): same skeleton, every row valid
 __global__ void __launch_bounds__(CR_THREADS)
-colsum_partial_kernel(const __nv_bfloat16* __restrict__ y, RowGeom g, int C, float* __restrict__ part) {
+colsum_partial_kernel(const __nv_bfloat16* __restrict__ y, long long ld, RowGeom g, int C, float* __restrict__ part) {
     col_reduce<1>(g, C, part, [&](long long m, int c, float (&acc)[1][2]) {
-        const float2 v = ld2(y + m * C + c);
+        const float2 v = ld2(y + m * ld + c);
         acc[0][0] += v.x; acc[0][1] += v.y;
     });
 }
@@ -250,13 +250,29 @@ bn_act_bwd_apply_kernel(BnSide a, BnSide r, int res_mode, const __nv_bfloat16* _
 
 // out[k][c] = sum over slabs of part[slab][k][c]
 __global__ void sum_partials_kernel(const float* __restrict__ part, int nslabs, int nacc, int C,
-                                    float* __restrict__ out) {
+                                    float* __restrict__ out, int accumulate = 0) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     for (int k = 0; k < nacc; ++k) {
         float t = 0.0f;
         for (int b = 0; b < nslabs; ++b) t += part[((long long)b * nacc + k) * C + c];
-        out[(long long)k * C + c] = t;
+        float* o = out + (long long)k * C + c;
+        *o = accumulate ? *o + t : t;
+    }
+}
+
+// dst[i] (+)= sum_s part[s][i]  (split-K weight-gradient partials folded into the gradient buffer)
+__global__ void __launch_bounds__(256)
+accumulate_partials_kernel(const float* __restrict__ part, int s, long long n4, float* __restrict__ dst, int accumulate) {
+    const float4* p4 = reinterpret_cast<const float4*>(part);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 a = accumulate ? d4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < s; ++k) {
+            const float4 v = __ldg(p4 + (long long)k * n4 + i);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        d4[i] = a;
     }
 }
 
@@ -547,10 +563,23 @@ int eegx_bn_stats_bf16(const void* y, int64_t B, int64_t T, int64_t pad, int64_t
     return EEGX_OK;
 }
 
-int eegx_colsum_bf16(const void* y, int64_t rows, int64_t C, float* out, void* workspace, size_t workspace_bytes,
-                     void* stream) {
+int eegx_accumulate_partials_f32(const float* part, int64_t s, int64_t n, float* dst, int accumulate, void* stream) {
     if (int rc = eegx::require_sm100()) return rc;
-    EEGX_REQUIRE(rows >= 0 && C >= 2 && (C % 2) == 0, EEGX_ERR_SHAPE, "colsum: C must be even");
+    EEGX_REQUIRE(s >= 1 && n >= 0 && (n % 4) == 0, EEGX_ERR_SHAPE, "accumulate_partials: n must be a multiple of 4");
+    if (n == 0) return EEGX_OK;
+    EEGX_REQUIRE(part && dst, EEGX_ERR_ARG, "accumulate_partials: NULL pointer");
+    EEGX_REQUIRE(eegx::aligned16(part) && eegx::aligned16(dst), EEGX_ERR_ALIGN, "accumulate_partials: 16-byte alignment");
+    accumulate_partials_kernel<<<ew_grid(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(part, (int)s, n / 4, dst,
+                                                                                              accumulate);
+    EEGX_CUDA_CHECK(cudaGetLastError());
+    return EEGX_OK;
+}
+
+int eegx_colsum_bf16(const void* y, int64_t ld, int64_t rows, int64_t C, float* out, int accumulate, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+    if (int rc = eegx::require_sm100()) return rc;
+    EEGX_REQUIRE(rows >= 0 && C >= 2 && (C % 2) == 0 && ld >= C && (ld % 2) == 0, EEGX_ERR_SHAPE,
+                 "colsum: C and ld must be even, ld >= C");
     EEGX_REQUIRE(y && out && workspace, EEGX_ERR_ARG, "colsum: NULL pointer");
     EEGX_REQUIRE(workspace_bytes >= eegx_colreduce_workspace_bytes(C), EEGX_ERR_WORKSPACE, "colsum: workspace too small");
     const RowGeom g{(long long)rows, 1, 0, 1};
@@ -558,8 +587,8 @@ int eegx_colsum_bf16(const void* y, int64_t rows, int64_t C, float* out, void* w
     const int slabs = slabs_for(g.M, (int)C);
     float* part = static_cast<float*>(workspace);
     dim3 grid((unsigned)((C + CR_COLS - 1) / CR_COLS), (unsigned)slabs);
-    colsum_partial_kernel<<<grid, CR_THREADS, 0, st>>>(static_cast<const __nv_bfloat16*>(y), g, (int)C, part);
-    sum_partials_kernel<<<(int)((C + 127) / 128), 128, 0, st>>>(part, slabs, 1, (int)C, out);
+    colsum_partial_kernel<<<grid, CR_THREADS, 0, st>>>(static_cast<const __nv_bfloat16*>(y), ld, g, (int)C, part);
+    sum_partials_kernel<<<(int)((C + 127) / 128), 128, 0, st>>>(part, slabs, 1, (int)C, out, accumulate);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
 }

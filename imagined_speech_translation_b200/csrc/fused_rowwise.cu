@@ -166,7 +166,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
 // each sum every 8th block (coalesced 128-byte rows), then the warps are added in order.
 __global__ void __launch_bounds__(256)
 colsum_partials_kernel(const float* __restrict__ part, int nblocks, int nvec, int C,
-                       float* __restrict__ out0, float* __restrict__ out1) {
+                       float* __restrict__ out0, float* __restrict__ out1, int accumulate) {
     __shared__ float red[8][32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + lane, j = blockIdx.y;
@@ -179,7 +179,8 @@ colsum_partials_kernel(const float* __restrict__ part, int nblocks, int nvec, in
         float r = 0.0f;
 #pragma unroll
         for (int w = 0; w < 8; ++w) r += red[w][lane];
-        (j == 0 ? out0 : out1)[c] = r;
+        float* o = (j == 0 ? out0 : out1) + c;
+        *o = accumulate ? *o + r : r;
     }
 }
 
@@ -358,8 +359,8 @@ size_t eegx_layernorm_bwd_workspace_bytes(int64_t C) {
 
 int eegx_layernorm_bwd_bf16(const void* dy, const void* x, const float* gamma, const float* beta,
                             const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
-                            void* workspace, size_t workspace_bytes, int64_t rows, int64_t C, int act,
-                            const uint64_t* rng_state, uint32_t site, float p, void* stream) {
+                            int accumulate, void* workspace, size_t workspace_bytes, int64_t rows, int64_t C,
+                            int act, const uint64_t* rng_state, uint32_t site, float p, void* stream) {
     if (int rc = eegx::require_sm100()) return rc;
     EEGX_REQUIRE(rows >= 0 && C >= 8 && C <= LN_MAX_C && (C % 8) == 0, EEGX_ERR_SHAPE,
                  "layernorm: C must be a multiple of 8 in [8, %d]", LN_MAX_C);
@@ -382,7 +383,7 @@ int eegx_layernorm_bwd_bf16(const void* dy, const void* x, const float* gamma, c
         case 5: case 6: launch_ln_bwd<6>(dy, x, gamma, beta, mean, rstd, dx, part, grid, rows, (int)C, act, dc, st); break;
         default: launch_ln_bwd<8>(dy, x, gamma, beta, mean, rstd, dx, part, grid, rows, (int)C, act, dc, st); break;
     }
-    colsum_partials_kernel<<<dim3((unsigned)((C + 31) / 32), 2), 256, 0, st>>>(part, grid, 2, (int)C, dgamma, dbeta);
+    colsum_partials_kernel<<<dim3((unsigned)((C + 31) / 32), 2), 256, 0, st>>>(part, grid, 2, (int)C, dgamma, dbeta, accumulate);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
 }

@@ -93,18 +93,36 @@ def _f32(p: torch.Tensor) -> torch.Tensor:
     return p if p.dtype == torch.float32 and p.is_contiguous() else p.float().contiguous()
 
 
-def colsum(y: torch.Tensor) -> torch.Tensor:
-    """Column sums (fp32) of a (rows, C) bf16 matrix: bias gradients, fixed summation order."""
-    _need(y, "y")
+def grad_buffer(p) -> Optional[torch.Tensor]:
+    """The parameter's existing gradient buffer if a kernel may accumulate into it in place (fp32,
+    contiguous, CUDA) -- the flat buffers of FlatAdamW qualify -- else None (autograd accumulates)."""
+    g = getattr(p, "grad", None)
+    if g is None or not p.is_leaf or g.dtype != torch.float32 or not g.is_cuda or not g.is_contiguous():
+        return None
+    return g
+
+
+def colsum(y: torch.Tensor, into: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """Column sums (fp32) of a (rows, C) bf16 matrix (unit column stride): bias gradients, fixed
+    summation order.  into: gradient buffer to accumulate into (then None is returned)."""
+    if not y.is_cuda or y.dtype != torch.bfloat16 or y.stride(1) != 1:
+        raise ValueError("colsum needs a CUDA bf16 matrix with unit column stride")
     rows, C_ = y.shape
-    out = torch.empty(C_, dtype=torch.float32, device=y.device)
+    out = into if into is not None else torch.empty(C_, dtype=torch.float32, device=y.device)
     if rows == 0:
-        return out.zero_()
+        return None if into is not None else out.zero_()
     lib = _lib.lib()
     ws = _workspace(lib.eegx_colreduce_workspace_bytes(C_), y.device)
-    _lib.check(lib.eegx_colsum_bf16(_lib.ptr(y), rows, C_, _lib.ptr(out), _lib.ptr(ws), ws.numel(),
-                                    _lib.stream_ptr()), "eegx_colsum_bf16")
-    return out
+    _lib.check(lib.eegx_colsum_bf16(_lib.ptr(y), y.stride(0), rows, C_, _lib.ptr(out), int(into is not None),
+                                    _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "eegx_colsum_bf16")
+    return None if into is not None else out
+
+
+def accumulate_partials(part: torch.Tensor, into: torch.Tensor) -> None:
+    """into += part.sum(0) for fp32 split-K partials (s, ...) in one pass."""
+    s = part.shape[0]
+    _lib.check(_lib.lib().eegx_accumulate_partials_f32(_lib.ptr(part), s, part.numel() // s, _lib.ptr(into), 1,
+                                                       _lib.stream_ptr()), "eegx_accumulate_partials_f32")
 
 
 # ------------------------------------------------------------------------------------------ LayerNorm
@@ -133,14 +151,18 @@ class _LayerNorm(torch.autograd.Function):
         rows = x.numel() // C_
         dy = dy.contiguous()
         dx = torch.empty_like(x)
-        dg = torch.empty(C_, dtype=torch.float32, device=x.device)
-        db = torch.empty_like(dg)
+        gw, gb = grad_buffer(weight), grad_buffer(bias)
+        fused_acc = gw is not None and gb is not None      # write d(gamma), d(beta) straight into the gradients
+        dg = gw if fused_acc else torch.empty(C_, dtype=torch.float32, device=x.device)
+        db = gb if fused_acc else torch.empty_like(dg)
         lib = _lib.lib()
         ws = _workspace(lib.eegx_layernorm_bwd_workspace_bytes(C_), x.device)
         _lib.check(lib.eegx_layernorm_bwd_bf16(
             _lib.ptr(dy), _lib.ptr(x), _lib.ptr(_f32(weight)), _lib.ptr(_f32(bias)), _lib.ptr(mean), _lib.ptr(rstd),
-            _lib.ptr(dx), _lib.ptr(dg), _lib.ptr(db), _lib.ptr(ws), ws.numel(), rows, C_, act, _lib.ptr(rng), site, p,
-            _lib.stream_ptr()), "eegx_layernorm_bwd_bf16")
+            _lib.ptr(dx), _lib.ptr(dg), _lib.ptr(db), int(fused_acc), _lib.ptr(ws), ws.numel(), rows, C_, act,
+            _lib.ptr(rng), site, p, _lib.stream_ptr()), "eegx_layernorm_bwd_bf16")
+        if fused_acc:
+            return dx, None, None, None, None, None, None, None
         return dx, dg.to(weight.dtype), db.to(bias.dtype), None, None, None, None, None
 
 

@@ -56,10 +56,12 @@ def _w_conv_dgrad(w):        # (Cout, Cin, k) -> (k*Cout, Cin) bf16 with taps fl
 
 
 
-def _wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+def _wgrad(dy: torch.Tensor, x: torch.Tensor, into: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
     """dW (N, K) fp32 = dy^T x, reduction over the R rows.  The output is small (N x K) while R is
     ~10^4, so a plain launch fills only N*K / (128*256) of the 148 SMs: split the reduction into s
-    row-chunks run as GEMM batches (s * tiles ~ one wave) and add the partials in a fixed order."""
+    row-chunks run as GEMM batches (s * tiles ~ one wave) and add the partials in a fixed order.
+    into: an (N, K) fp32 gradient buffer to accumulate into (GEMM epilogue `D += ...` / one
+    partial-folding pass); then None is returned and autograd has nothing left to add."""
     R, N = dy.shape
     K = x.shape[1]
     bn = 64 if K <= 64 else (256 if K > 128 and (K % 256 == 0 or K >= 1024) else 128)
@@ -68,12 +70,24 @@ def _wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     while tiles * s * 2 <= 160 and R % (s * 2) == 0 and (R // (s * 2)) % 8 == 0 and R // (s * 2) >= 512:
         s *= 2
     if s == 1:
+        if into is not None:
+            ops.gemm(dy, x, a_mn_major=True, b_mn_major=True, out=into, accumulate=True)
+            return None
         return ops.gemm(dy, x, a_mn_major=True, b_mn_major=True, out_dtype=torch.float32)
     chunk = R // s
     dy3 = dy.as_strided((s, chunk, N), (chunk * dy.stride(0), dy.stride(0), 1), dy.storage_offset())
     x3 = x.as_strided((s, chunk, K), (chunk * x.stride(0), x.stride(0), 1), x.storage_offset())
     part = ops.gemm(dy3, x3, a_mn_major=True, b_mn_major=True, out_dtype=torch.float32)      # (s, N, K)
+    if into is not None and (N * K) % 4 == 0:
+        fused.accumulate_partials(part, into)
+        return None
     return part.sum(0)
+
+
+def _grad2d(w):
+    """(N, K) view of a 2-D weight's in-place gradient buffer, or None."""
+    g = fused.grad_buffer(w)
+    return g if g is not None and g.dim() == 2 else None
 
 
 class _Linear(torch.autograd.Function):
@@ -96,6 +110,7 @@ class _Linear(torch.autograd.Function):
             y = ops.gemm(x, w16, b32)
             ctx.save_for_backward(x, weight, None)
         ctx.has_bias = bias is not None
+        ctx.bias_ref = bias
         ctx.gelu = gelu
         ctx.n_pad = n_pad
         return y[:, :N] if n_pad else y
@@ -115,9 +130,13 @@ class _Linear(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = ops.gemm(dy, w16, b_mn_major=True)                                   # (M,N) @ (N,K)
         if ctx.needs_input_grad[1]:
-            dw = _wgrad(dy, x)[:N]                                                       # dy^T @ x
+            into = _grad2d(weight) if ctx.n_pad == 0 else None
+            dw = _wgrad(dy, x, into)                                                     # dy^T @ x
+            dw = dw[:N] if dw is not None else None
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = fused.colsum(dy)[:N]
+            gb = fused.grad_buffer(ctx.bias_ref) if ctx.n_pad == 0 else None
+            db = fused.colsum(dy, gb)
+            db = db[:N] if db is not None else None
         return dx, dw, db, None
 
 
@@ -210,17 +229,23 @@ class _LinearCat(torch.autograd.Function):
         bcat = torch.cat([b.detach().float() for b in bs])
         y = ops.gemm(x, _w_cat(ws), bcat)
         ctx.save_for_backward(x, *ws)
+        ctx.biases = bs
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, *ws = ctx.saved_tensors
+        bs = ctx.biases
         dy = dy.contiguous()
         dx = ops.gemm(dy, _w_cat(ws), b_mn_major=True) if ctx.needs_input_grad[0] else None
-        dw = _wgrad(dy, x)
-        db = fused.colsum(dy)
-        sizes = [w.shape[0] for w in ws]
-        return (dx, *dw.split(sizes, 0), *db.split(sizes, 0))
+        dws, dbs, off = [], [], 0
+        for w, b in zip(ws, bs):
+            n = w.shape[0]
+            sl = dy[:, off:off + n]                       # column block of dy: row pitch = total N
+            dws.append(_wgrad(sl, x, _grad2d(w)))
+            dbs.append(fused.colsum(sl, fused.grad_buffer(b)))
+            off += n
+        return (dx, *dws, *dbs)
 
 
 def linear_cat(x: torch.Tensor, *wb) -> torch.Tensor:

@@ -185,10 +185,11 @@ int eegx_layernorm_fwd_bf16(const void* x, const float* gamma, const float* beta
                             float* rstd, int64_t rows, int64_t C, float eps, int act, const uint64_t* rng_state,
                             uint32_t site, float p, void* stream);
 size_t eegx_layernorm_bwd_workspace_bytes(int64_t C);
+/* accumulate != 0: dgamma / dbeta += (they may point straight into the parameters' gradient buffers). */
 int eegx_layernorm_bwd_bf16(const void* dy, const void* x, const float* gamma, const float* beta,
                             const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
-                            void* workspace, size_t workspace_bytes, int64_t rows, int64_t C, int act,
-                            const uint64_t* rng_state, uint32_t site, float p, void* stream);
+                            int accumulate, void* workspace, size_t workspace_bytes, int64_t rows, int64_t C,
+                            int act, const uint64_t* rng_state, uint32_t site, float p, void* stream);
 
 /* out = a + scale * dropout(b): the residual adds of layers.py:234, 242, 251 / brain_encoder.py:165. */
 int eegx_add_dropout_fwd_bf16(const void* a, const void* b, void* out, int64_t n, float scale,
@@ -211,10 +212,12 @@ int eegx_glu_bwd_bf16(const void* dout, const void* ag, void* dag, int64_t rows,
  * mean / rstd (C) fp32; running_mean / running_var updated in place with `momentum` (unbiased
  * variance) unless NULL.  Two fixed-order stages (bit-stable). */
 size_t eegx_colreduce_workspace_bytes(int64_t C);
-/* out[c] = sum_r y[r, c] of a (rows, C) bf16 matrix, fp32, fixed order: the bias gradients of nn.Linear /
- * nn.Conv1d. */
-int eegx_colsum_bf16(const void* y, int64_t rows, int64_t C, float* out, void* workspace, size_t workspace_bytes,
-                     void* stream);
+/* out[c] (+)= sum_r y[r * ld + c] of a (rows, C) bf16 matrix with row pitch ld, fp32, fixed order: the bias
+ * gradients of nn.Linear / nn.Conv1d (accumulate != 0: added into the gradient buffer). */
+int eegx_colsum_bf16(const void* y, int64_t ld, int64_t rows, int64_t C, float* out, int accumulate, void* workspace,
+                     size_t workspace_bytes, void* stream);
+/* dst[i] (+)= sum_s part[s * n + i]: folds the split-K partials of a weight-gradient GEMM into the gradient. */
+int eegx_accumulate_partials_f32(const float* part, int64_t s, int64_t n, float* dst, int accumulate, void* stream);
 int eegx_bn_stats_bf16(const void* y, int64_t B, int64_t T, int64_t pad, int64_t C, float eps, float* mean,
                        float* rstd, float* running_mean, float* running_var, float momentum, void* workspace,
                        size_t workspace_bytes, void* stream);
