@@ -20,6 +20,7 @@
 //              128-bit global stores; then hand the TMEM stage back ("tmem_empty").
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "eegx_common.h"
 
@@ -135,6 +136,71 @@ __device__ __forceinline__ unsigned long long make_smem_desc(unsigned saddr, uns
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+// Epilogue of one accumulator tile for the 32 rows a warp owns: TMEM -> registers, alpha / bias /
+// GELU / accumulate, convert, 128-bit stores.  `row` is this lane's output row, n_base the tile's first column.
+template <int BLOCK_N>
+__device__ __forceinline__ void epilogue_rows(const GemmParams& p, unsigned taddr, long long row, long long n_base,
+                                              long long bi) {
+    const bool row_ok = row < p.M;
+    #pragma unroll 1
+                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                    float v[32];
+                    tmem_ld32(taddr + c * 32, v);
+                    const long long col0 = n_base + c * 32;
+                    if (row_ok && col0 < p.N) {
+                        const bool full = col0 + 32 <= p.N;
+    #pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
+                        if (p.epilogue >= 1) {
+    #pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (full || col0 + i < p.N) v[i] += __ldg(p.bias + col0 + i);
+                        }
+                        if (p.epilogue == 2) {
+    #pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+                        }
+                        const long long off = bi * p.stride_d + row * p.ldd + col0;
+                        if (p.out_f32) {
+                            float* d = reinterpret_cast<float*>(p.D) + off;
+                            if (full && (p.ldd & 3) == 0) {
+    #pragma unroll
+                                for (int i = 0; i < 32; i += 4) {
+                                    float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                                    if (p.accumulate) {
+                                        const float4 old = *reinterpret_cast<const float4*>(d + i);
+                                        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                                    }
+                                    *reinterpret_cast<float4*>(d + i) = o;
+                                }
+                            } else {
+                                for (int i = 0; i < 32; ++i)
+                                    if (col0 + i < p.N) d[i] = p.accumulate ? d[i] + v[i] : v[i];
+                            }
+                        } else {
+                            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + off;
+                            if (full && (p.ldd & 7) == 0 && !p.accumulate) {
+    #pragma unroll
+                                for (int i = 0; i < 32; i += 8) {
+                                    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i], v[i + 1]);
+                                    __nv_bfloat162 h1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
+                                    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]);
+                                    __nv_bfloat162 h3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
+                                    uint4 o;
+                                    o.x = *reinterpret_cast<unsigned*>(&h0); o.y = *reinterpret_cast<unsigned*>(&h1);
+                                    o.z = *reinterpret_cast<unsigned*>(&h2); o.w = *reinterpret_cast<unsigned*>(&h3);
+                                    *reinterpret_cast<uint4*>(d + i) = o;
+                                }
+                            } else {
+                                for (int i = 0; i < 32; ++i)
+                                    if (col0 + i < p.N)
+                                        d[i] = __float2bfloat16(p.accumulate ? __bfloat162float(d[i]) + v[i] : v[i]);
+                            }
+                        }
+                    }
+                }
+}
+
 template <int BLOCK_N, int STAGES>
 struct SmemLayout {
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
@@ -162,7 +228,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     unsigned* tmem_ptr_smem = reinterpret_cast<unsigned*>(smem + L::BAR_OFFSET + L::NUM_BARS * 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr unsigned TMEM_COLS = 2 * BLOCK_N;   // two accumulator stages (power of two >= 32)
+    constexpr unsigned TMEM_COLS = BLOCK_N <= 64 ? 128 : (BLOCK_N <= 128 ? 256 : 512);   // two accumulator stages, power of two
 
     const long long m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
     const long long n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
@@ -274,65 +340,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             mbar_wait(tmem_full_bar(acc), acc_phase);
             tc_fence_after();
             const long long row = (long long)m_blk * BLOCK_M + quarter * 32 + lane;
-            const bool row_ok = row < p.M;
             const unsigned taddr = tmem_base + acc * BLOCK_N + ((unsigned)(quarter * 32) << 16);
-#pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 32; ++c) {
-                float v[32];
-                tmem_ld32(taddr + c * 32, v);
-                const long long col0 = (long long)n_blk * BLOCK_N + c * 32;
-                if (row_ok && col0 < p.N) {
-                    const bool full = col0 + 32 <= p.N;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
-                    if (p.epilogue >= 1) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (full || col0 + i < p.N) v[i] += __ldg(p.bias + col0 + i);
-                    }
-                    if (p.epilogue == 2) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-                    }
-                    const long long off = bi * p.stride_d + row * p.ldd + col0;
-                    if (p.out_f32) {
-                        float* d = reinterpret_cast<float*>(p.D) + off;
-                        if (full && (p.ldd & 3) == 0) {
-#pragma unroll
-                            for (int i = 0; i < 32; i += 4) {
-                                float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                                if (p.accumulate) {
-                                    const float4 old = *reinterpret_cast<const float4*>(d + i);
-                                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                                }
-                                *reinterpret_cast<float4*>(d + i) = o;
-                            }
-                        } else {
-                            for (int i = 0; i < 32; ++i)
-                                if (col0 + i < p.N) d[i] = p.accumulate ? d[i] + v[i] : v[i];
-                        }
-                    } else {
-                        __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + off;
-                        if (full && (p.ldd & 7) == 0 && !p.accumulate) {
-#pragma unroll
-                            for (int i = 0; i < 32; i += 8) {
-                                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i], v[i + 1]);
-                                __nv_bfloat162 h1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
-                                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]);
-                                __nv_bfloat162 h3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
-                                uint4 o;
-                                o.x = *reinterpret_cast<unsigned*>(&h0); o.y = *reinterpret_cast<unsigned*>(&h1);
-                                o.z = *reinterpret_cast<unsigned*>(&h2); o.w = *reinterpret_cast<unsigned*>(&h3);
-                                *reinterpret_cast<uint4*>(d + i) = o;
-                            }
-                        } else {
-                            for (int i = 0; i < 32; ++i)
-                                if (col0 + i < p.N)
-                                    d[i] = __float2bfloat16(p.accumulate ? __bfloat162float(d[i]) + v[i] : v[i]);
-                        }
-                    }
-                }
-            }
+            epilogue_rows<BLOCK_N>(p, taddr, row, (long long)n_blk * BLOCK_N, bi);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
@@ -343,6 +352,224 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+
+// ==================================================================================================
+// CTA-pair variant (tcgen05 cta_group::2): a cluster of two CTAs computes a 256 x BLOCK_N tile.
+// Each CTA stages its own 128 rows of A and HALF of the B tile (BLOCK_N / 2 rows), the leader CTA
+// issues one tcgen05.mma.cta_group::2 per 16-wide k slice that reads both CTAs' shared memory and
+// writes 128 accumulator rows into each CTA's TMEM.  Operand bytes fetched per MAC drop by a third
+// against the 1-CTA 128 x 256 tile, which is what bounds this kernel: the L2 -> SM path, not the
+// tensor pipe (B300_MICROARCH.md "LTS throughput cap").
+//   full barrier   lives in the leader; the leader's producer arms it with the bytes of BOTH CTAs,
+//                  and both CTAs' TMA loads complete on it (2-SM TMA form, peer bit cleared).
+//   empty / tmem_full barriers exist in both CTAs; the leader's tcgen05.commit multicasts to both.
+//   tmem_empty     lives in the leader; the epilogue warps of both CTAs arrive on it (the peer remotely).
+// ==================================================================================================
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(unsigned dst, const CUtensorMap* map, unsigned leader_bar, int c0,
+                                                int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2),
+          "l"(0x1000000000000000ull)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(unsigned smem_dst, unsigned ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(unsigned taddr, unsigned ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
+                                              unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Arrive (once the previously issued MMAs retire) on the barrier at this offset in BOTH CTAs of the pair.
+__device__ __forceinline__ void umma_commit_2sm(unsigned bar) {
+    asm volatile(
+        "{\n\t.reg .b16 m;\n\tmov.b16 m, 3;\n\t"
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
+        ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta0(unsigned bar) {
+    asm volatile(
+        "{\n\t.reg .b32 rem;\n\t"
+        "mapa.shared::cluster.u32 rem, %0, 0;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [rem];\n\t}" ::"r"(bar) : "memory");
+}
+
+template <int BLOCK_N, int STAGES>
+struct SmemLayout2 {
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+    static constexpr int B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int NUM_BARS = 2 * STAGES + 4;
+    static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;
+};
+
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  const GemmParams p) {
+    using L = SmemLayout2<BLOCK_N, STAGES>;
+    constexpr int HALF_N = BLOCK_N / 2;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const unsigned smem_base = smem_u32(smem);
+    const unsigned bar_base = smem_base + L::BAR_OFFSET;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tmem_full_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+    auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+    unsigned* tmem_ptr_smem = reinterpret_cast<unsigned*>(smem + L::BAR_OFFSET + L::NUM_BARS * 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    constexpr unsigned TMEM_COLS = BLOCK_N <= 128 ? 256 : 512;   // two accumulator stages, power of two
+
+    const long long m_blocks = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+    const long long n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
+    const long long tiles_per_batch = m_blocks * n_blocks;
+    const long long num_tiles = tiles_per_batch * p.batch;
+    const int num_kb = (int)((p.K + BLOCK_K - 1) / BLOCK_K);
+    const long long cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<unsigned long long>(&map_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<unsigned long long>(&map_b)) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tmem_full_bar(s), 1);
+            mbar_init(tmem_empty_bar(s), 2 * NUM_EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc_2sm(smem_u32(tmem_ptr_smem), TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const unsigned tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            int stage = 0;
+            unsigned phase = 0;
+            for (long long tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                const long long bi = tile / tiles_per_batch;
+                const long long rem = tile - bi * tiles_per_batch;
+                const int n_blk = (int)(rem / m_blocks), m_blk = (int)(rem % m_blocks);
+                const int m0 = m_blk * 2 * BLOCK_M + (int)rank * BLOCK_M;
+                const int n0 = n_blk * BLOCK_N + (int)rank * HALF_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const unsigned a_dst = smem_base + stage * L::STAGE_BYTES;
+                    const unsigned b_dst = a_dst + L::A_BYTES;
+                    const unsigned lead_full = full_bar(stage) & 0xFEFFFFFFu;     // the leader's barrier (peer bit cleared)
+                    if (leader) mbar_expect_tx(full_bar(stage), 2 * L::STAGE_BYTES);
+                    if (!A_MN) {
+                        tma_load_3d_2sm(a_dst, &map_a, lead_full, kb * BLOCK_K, m0, (int)bi);
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < BLOCK_M / 64; ++h)
+                            tma_load_3d_2sm(a_dst + h * (64 * BLOCK_K * 2), &map_a, lead_full, m0 + h * 64, kb * BLOCK_K, (int)bi);
+                    }
+                    if (!B_MN) {
+                        tma_load_3d_2sm(b_dst, &map_b, lead_full, kb * BLOCK_K, n0, (int)bi);
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < HALF_N / 64; ++h)
+                            tma_load_3d_2sm(b_dst + h * (64 * BLOCK_K * 2), &map_b, lead_full, n0 + h * 64, kb * BLOCK_K, (int)bi);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader && lane == 0) {
+            const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                                   ((B_MN ? 1u : 0u) << 16) | ((unsigned)(BLOCK_N >> 3) << 17) |
+                                   ((unsigned)((2 * BLOCK_M) >> 4) << 24);
+            int stage = 0;
+            unsigned phase = 0;
+            int acc = 0;
+            unsigned acc_phase = 0;
+            for (long long tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);
+                tc_fence_after();
+                const unsigned tmem_d = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const unsigned a_addr = smem_base + stage * L::STAGE_BYTES;
+                    const unsigned b_addr = a_addr + L::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const unsigned long long adesc =
+                            A_MN ? make_smem_desc(a_addr + k * 2048, 64 * BLOCK_K * 2, 1024)
+                                 : make_smem_desc(a_addr + k * 32, 16, 1024);
+                        const unsigned long long bdesc =
+                            B_MN ? make_smem_desc(b_addr + k * 2048, 64 * BLOCK_K * 2, 1024)
+                                 : make_smem_desc(b_addr + k * 32, 16, 1024);
+                        umma_bf16_2sm(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit_2sm(empty_bar(stage));
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_2sm(tmem_full_bar(acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5, both CTAs) =====================
+        const int quarter = warp & 3;
+        int acc = 0;
+        unsigned acc_phase = 0;
+        for (long long tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            const long long bi = tile / tiles_per_batch;
+            const long long rem = tile - bi * tiles_per_batch;
+            const int n_blk = (int)(rem / m_blocks), m_blk = (int)(rem % m_blocks);
+            mbar_wait(tmem_full_bar(acc), acc_phase);
+            tc_fence_after();
+            const long long row = (long long)m_blk * 2 * BLOCK_M + (long long)rank * BLOCK_M + quarter * 32 + lane;
+            const unsigned taddr = tmem_base + acc * BLOCK_N + ((unsigned)(quarter * 32) << 16);
+            epilogue_rows<BLOCK_N>(p, taddr, row, (long long)n_blk * BLOCK_N, bi);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (leader) mbar_arrive(tmem_empty_bar(acc));
+                else mbar_arrive_cta0(tmem_empty_bar(acc));
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
 }
 
 // ------------------------------------------------------------------ host side
@@ -390,6 +617,25 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, in
     return EEGX_OK;
 }
 
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
+int launch2(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int grid, cudaStream_t st) {
+    using L = SmemLayout2<BLOCK_N, STAGES>;
+    auto kern = gemm2_bf16_kernel<BLOCK_N, STAGES, A_MN, B_MN>;
+    EEGX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(ma, mb, p);
+    EEGX_CUDA_CHECK(cudaGetLastError());
+    return EEGX_OK;
+}
+
+template <int BLOCK_N, int STAGES>
+int dispatch_major2(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p,
+                    int grid, cudaStream_t st) {
+    if (!a_mn && !b_mn) return launch2<BLOCK_N, STAGES, false, false>(ma, mb, p, grid, st);
+    if (!a_mn && b_mn) return launch2<BLOCK_N, STAGES, false, true>(ma, mb, p, grid, st);
+    if (a_mn && !b_mn) return launch2<BLOCK_N, STAGES, true, false>(ma, mb, p, grid, st);
+    return launch2<BLOCK_N, STAGES, true, true>(ma, mb, p, grid, st);
+}
+
 template <int BLOCK_N, int STAGES>
 int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p,
                    int grid, cudaStream_t st) {
@@ -420,18 +666,47 @@ extern "C" int eegx_gemm_bf16(const eegx_gemm_desc* d, const void* A, const void
                  "leading dimensions too small (lda=%lld ldb=%lld ldd=%lld)", (long long)d->lda,
                  (long long)d->ldb, (long long)d->ldd);
 
-    // tile width: the widest N tile that does not waste more than it saves
+    // Tile width by a wave-quantisation cost model: a launch takes `rounds` passes of the 148 SMs (74 CTA
+    // pairs) over the tiles and a pass costs ~ BLOCK_N x a per-width efficiency factor (narrow tiles
+    // move more operand bytes per MAC; measured with tools/bench_gemm.py).
+    static const int env_2cta = [] { const char* v = getenv("EEGX_GEMM_2CTA"); return v ? atoi(v) : 1; }();
+    const bool bm_ = d->b_mn_major != 0;
+    auto rounds_for = [&](int bn, bool pr) {
+        const long long mb_ = pr ? (d->M + 2 * BLOCK_M - 1) / (2 * BLOCK_M) : (d->M + BLOCK_M - 1) / BLOCK_M;
+        const long long t = mb_ * ((d->N + bn - 1) / bn) * d->batch;
+        const long long slots = pr ? eegx::kNumSMsB200 / 2 : eegx::kNumSMsB200;
+        return (double)((t + slots - 1) / slots);
+    };
+    // CTA pairs (cta_group::2, 256-row tiles) pay off on the large problems only (tools/bench_gemm.py:
+    // +16 % on the 4096 x 51264 x 768 LM head, +5 % at 8192^3, -3..6 % on the 768-wide encoder GEMMs, and
+    // the pairs co-schedule worse when four region streams share the GPU): EEGX_GEMM_2CTA=2 forces them.
+    const bool want_pair = env_2cta != 0 && d->M > BLOCK_M && (env_2cta >= 2 || d->N >= 8192 || d->K >= 4096);
     int block_n = 128;
-    if (d->N <= 64) block_n = 64;
-    else if (d->N > 128 && (d->N % 256 == 0 || d->N >= 1024)) block_n = 256;
-    if (d->force_block_n == 64 || d->force_block_n == 128 || d->force_block_n == 256) block_n = d->force_block_n;
+    {
+        const int cand[4] = {64, 128, 192, 256};
+        const double eff[4] = {1.7, 1.22, 1.04, 1.0};
+        double best = 1e300;
+        for (int i = 0; i < 4; ++i) {
+            const int bn = cand[i];
+            if (bn == 64 && d->N > 64) continue;                       // 64 only for very narrow outputs
+            if (bn > 64 && d->N <= 64) continue;
+            if (bn == 192) continue;                                   // measured slower than 256 (kept for force_block_n)
+            const bool pr = want_pair && bn >= 128;
+            const double c = rounds_for(bn, pr) * (bn + 16) * eff[i];
+            if (c < best) { best = c; block_n = bn; }
+        }
+    }
+    if (d->force_block_n == 64 || d->force_block_n == 128 || d->force_block_n == 192 || d->force_block_n == 256)
+        block_n = d->force_block_n;
+    const bool pair = want_pair && block_n >= 128 && !(block_n == 192 && bm_);
+    const int b_box_rows = pair ? block_n / 2 : block_n;
 
     CUtensorMap ma, mb;
     int rc;
     if (!d->a_mn_major) rc = make_map(&ma, A, d->K, d->M, d->batch, d->lda, d->stride_a, BLOCK_K, BLOCK_M);
     else rc = make_map(&ma, A, d->M, d->K, d->batch, d->lda, d->stride_a, 64, BLOCK_K);
     if (rc) return rc;
-    if (!d->b_mn_major) rc = make_map(&mb, B, d->K, d->N, d->batch, d->ldb, d->stride_b, BLOCK_K, block_n);
+    if (!d->b_mn_major) rc = make_map(&mb, B, d->K, d->N, d->batch, d->ldb, d->stride_b, BLOCK_K, b_box_rows);
     else rc = make_map(&mb, B, d->N, d->K, d->batch, d->ldb, d->stride_b, 64, BLOCK_K);
     if (rc) return rc;
 
@@ -442,15 +717,28 @@ extern "C" int eegx_gemm_bf16(const eegx_gemm_desc* d, const void* A, const void
     p.out_f32 = d->out_f32; p.epilogue = d->epilogue; p.accumulate = d->accumulate;
     p.alpha = d->alpha;
 
-    const long long m_blocks = (d->M + BLOCK_M - 1) / BLOCK_M;
-    const long long n_blocks = (d->N + block_n - 1) / block_n;
-    const long long tiles = m_blocks * n_blocks * d->batch;
-    const int grid = (int)(tiles < eegx::kNumSMsB200 ? tiles : eegx::kNumSMsB200);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool am = d->a_mn_major != 0, bm = d->b_mn_major != 0;
+    const long long n_blocks = (d->N + block_n - 1) / block_n;
+    if (pair) {
+        const long long m_blocks2 = (d->M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+        const long long tiles2 = m_blocks2 * n_blocks * d->batch;
+        const long long max_clusters = eegx::kNumSMsB200 / 2;
+        const int grid2 = 2 * (int)(tiles2 < max_clusters ? tiles2 : max_clusters);
+        if (block_n == 128) return dispatch_major2<128, 8>(am, bm, ma, mb, p, grid2, st);
+        if (block_n == 192) {      // K-major B only (see above)
+            if (am) return launch2<192, 7, true, false>(ma, mb, p, grid2, st);
+            return launch2<192, 7, false, false>(ma, mb, p, grid2, st);
+        }
+        return dispatch_major2<256, 6>(am, bm, ma, mb, p, grid2, st);
+    }
+    const long long m_blocks = (d->M + BLOCK_M - 1) / BLOCK_M;
+    const long long tiles = m_blocks * n_blocks * d->batch;
+    const int grid = (int)(tiles < eegx::kNumSMsB200 ? tiles : eegx::kNumSMsB200);
     switch (block_n) {
         case 64: return dispatch_major<64, 8>(am, bm, ma, mb, p, grid, st);
         case 128: return dispatch_major<128, 6>(am, bm, ma, mb, p, grid, st);
+        case 192: return dispatch_major<192, 5>(am, bm, ma, mb, p, grid, st);
         default: return dispatch_major<256, 4>(am, bm, ma, mb, p, grid, st);
     }
 }

@@ -135,7 +135,7 @@ typedef struct eegx_gemm_desc {
     int32_t out_f32;
     int32_t epilogue;
     int32_t accumulate;
-    int32_t force_block_n; /* 0 = auto; 64 / 128 / 256 pins the N tile (tests, tuning) */
+    int32_t force_block_n; /* 0 = auto (wave-quantisation cost model); 64 / 128 / 192 / 256 pins the N tile */
     float alpha;
     int32_t reserved;
 } eegx_gemm_desc;

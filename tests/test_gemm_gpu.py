@@ -36,7 +36,7 @@ def test_gemm_k_major(M, N, K, out_dtype):
     assert _rel(d, ref) <= tol
 
 
-@pytest.mark.parametrize("block_n", [64, 128, 256])
+@pytest.mark.parametrize("block_n", [64, 128, 192, 256])
 def test_gemm_tile_widths(block_n):
     a, b = _mk((512, 320), 3), _mk((512, 320), 4)
     d = ops.gemm(a, b, out_dtype=torch.float32, force_block_n=block_n)

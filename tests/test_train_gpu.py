@@ -93,3 +93,76 @@ def test_first_step_has_zero_lr():
     w0 = model.brain_encoder.region_encoders['frontal'].conv2.weight.detach().clone()
     t.train_epoch(0)
     assert torch.equal(model.brain_encoder.region_encoders['frontal'].conv2.weight, w0)
+
+
+def _zero_dropout(model):
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+        if isinstance(m, torch.nn.MultiheadAttention):
+            m.dropout = 0.0
+        if isinstance(m, torch.nn.TransformerEncoderLayer):
+            m.dropout.p = m.dropout1.p = m.dropout2.p = 0.0
+    dec = model.bart_decoder.bart.model.decoder
+    dec.dropout = 0.0
+    for layer in dec.layers:
+        layer.dropout = 0.0
+
+
+def test_high_density_long_window_step():
+    """BASELINE configs[3] shape at a small batch: 128 ch x 4096 samples, STFT n_fft=1024 hop=256
+    (generic DSP kernel) -> 4 regions of 32 x 513 feature channels x 17 frames -> one train step."""
+    C, T, B = 128, 4096, 2
+    counts = {'frontal': 32, 'temporal': 32, 'central': 32, 'parietal': 32}
+    fe = pkg.SpectrogramFrontEnd(C, T, pkg.DSP_CONFIG_LONG)
+    assert (fe.n_freqs, fe.n_frames) == (513, 17) and fe.kernel_name == "generic"
+    torch.manual_seed(0)
+    model = EEGDecodingModel(n_timepoints=fe.n_frames,
+                             region_channel_counts={k: v * fe.n_freqs for k, v in counts.items()}).cuda().train()
+    cfg = dict(tr.CONFIG, accumulation_steps=1, warmup_steps=1)
+    opt = tr.build_optimizer(model, cfg)
+    sched = tr.cosine_schedule_with_warmup(opt, 1, 10)
+    t = tr.EEGTrainer(model, None, None, None, opt, sched, cfg, front_end=fe, region_channel_counts=counts)
+    g = torch.Generator().manual_seed(5)
+    labels = torch.randint(1, 51271, (B, 16), generator=g)
+    labels[:, 10:] = -100
+    ids = torch.cat([torch.full((B, 1), 101), labels[:, :-1].clamp_min(0)], dim=1)
+    batch = {'raw': 20.0 * torch.randn(B, C, T, generator=g), 'decoder_input_ids': ids, 'labels': labels}
+    for _ in range(2):
+        loss = t.train_step(batch)
+        t._optimizer_step(step_scheduler=True)
+    assert torch.isfinite(loss) and abs(loss.item() - math.log(51271)) < 1.0
+    assert float(opt.grad_norm()) > 0.0
+
+
+def test_cuda_graph_replay_matches_eager():
+    counts = {'frontal': 16, 'temporal': 16, 'central': 16, 'parietal': 16}
+    torch.manual_seed(0)
+    model = EEGDecodingModel(n_timepoints=33, region_channel_counts=counts).cuda().train()
+    _zero_dropout(model)
+    cfg = dict(tr.CONFIG, accumulation_steps=1, warmup_steps=500)       # lr stays ~0: weights do not move
+    opt = tr.build_optimizer(model, cfg)
+    sched = tr.cosine_schedule_with_warmup(opt, 10 ** 9, 10 ** 9 + 1)
+    t = tr.EEGTrainer(model, None, None, None, opt, sched, cfg)
+    batches = [{k: (v if not isinstance(v, list) else [r.cuda() for r in v]) for k, v in b.items()}
+               for b in _batches(3, 4, counts, 33, seed=9)]
+    flat = [{'eeg0': b['eeg'][0], 'eeg1': b['eeg'][1], 'eeg2': b['eeg'][2], 'eeg3': b['eeg'][3],
+             'decoder_input_ids': b['decoder_input_ids'].cuda(), 'labels': b['labels'].cuda()} for b in batches]
+
+    class _T(tr.EEGTrainer):
+        def _regions(self, batch):
+            return [batch['eeg0'], batch['eeg1'], batch['eeg2'], batch['eeg3']]
+
+    t.__class__ = _T
+    eager = []
+    for b in flat:
+        eager.append(t.train_step(b).item())
+        gnorm_eager = None
+        t._optimizer_step(step_scheduler=False)
+        gnorm_eager = float(opt.grad_norm())
+    t.capture(flat[0])
+    for b, ref in zip(flat, eager):
+        loss = t.train_step(b)
+        t._optimizer_step(step_scheduler=False)
+        assert abs(loss.item() - ref) <= 2e-3 * abs(ref)
+    assert abs(float(opt.grad_norm()) - gnorm_eager) <= 2e-2 * gnorm_eager
