@@ -369,26 +369,31 @@ def run_ours(args, rank, world, local_rank):
                      "decoder_input_ids": ids.pin_memory(), "labels": labels.pin_memory()})
     loss_host = torch.zeros(max(args.steps, 2), pin_memory=True)
     copy_stream = torch.cuda.Stream()
-    staged = [None, None]
+    # two preallocated device staging sets (no allocator traffic inside the timed region)
+    dev_stage = [{n: torch.empty_like(t, device=dev) for n, t in host[k].items()} for k in range(2)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
     def stage(i):
         k = i % 2
+        copy_stream.wait_event(consumed[k])                 # the step that read this staging set has finished
         with torch.cuda.stream(copy_stream):
-            staged[k] = {n: t.to(dev, non_blocking=True) for n, t in host[k].items()}
+            for n, t in host[k].items():
+                dev_stage[k][n].copy_(t, non_blocking=True)
             ready[k].record(copy_stream)
 
     def e2e_steps(n):
+        cur = torch.cuda.current_stream()
+        consumed[0].record(cur)
+        consumed[1].record(cur)
         stage(0)
         for i in range(n):
             k = i % 2
-            torch.cuda.current_stream().wait_event(ready[k])
-            batch = staged[k]
+            cur.wait_event(ready[k])
             if i + 1 < n:
                 stage(i + 1)                                # H2D of the next batch overlaps this step
-            l = step(batch)
-            for t in batch.values():
-                t.record_stream(torch.cuda.current_stream())
+            l = step(dev_stage[k])
+            consumed[k].record(cur)
             loss_host[i % loss_host.numel()].copy_(l, non_blocking=True)     # D2H of the step's loss
 
     e2e_steps(2)
@@ -406,9 +411,13 @@ def run_ours(args, rank, world, local_rank):
 
     # ---------------- dominant kernel: per-launch GEMM timing pass (eager, outside the graph) ----------------
     # (single stream, so the events bracket exactly one GEMM and nothing runs beside it)
+    # and with the GPU kept ~150 ms behind the CPU, so the host-side work of a call -- tensor-map encode,
+    # launch -- never shows up between a GEMM's two events)
     trainer._graph = None
     model.brain_encoder.parallel_regions = False
     step(batches[0])
+    torch.cuda.synchronize()
+    torch.cuda._sleep(int(0.15 * 1.9e9))
     ops.GEMM_TIMING = []
     step(batches[0])
     torch.cuda.synchronize()

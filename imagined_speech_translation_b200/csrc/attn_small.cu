@@ -52,16 +52,22 @@ __device__ __forceinline__ void ldsm_x2_trans(uint32_t& b0, uint32_t& b1, const 
     asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];\n" : "=r"(b0), "=r"(b1) : "r"(addr));
 }
 
+// global (S rows x HD, row stride rs) -> shared tile (rows_pad x (HD + 8)), rows >= S zero filled.
+// cp.async (LDGSTS) 16-byte copies: every thread's copies are in flight together and the caller waits
+// once (cp_async_wait_all + __syncthreads) -- a register-staged loop exposed one global-memory latency
+// per iteration, which dominated these short kernels.
 template <int HD>
 __device__ __forceinline__ void load_tile(bf16* dst, const bf16* src, long long rs, int S, int rows_pad) {
     constexpr int V = HD / 8, LD = HD + 8;
     for (int idx = threadIdx.x; idx < rows_pad * V; idx += blockDim.x) {
         const int r = idx / V, v = idx % V;
-        uint4 val = make_uint4(0u, 0u, 0u, 0u);
-        if (r < S) val = *reinterpret_cast<const uint4*>(src + (long long)r * rs + v * 8);
-        *reinterpret_cast<uint4*>(dst + r * LD + v * 8) = val;
+        const unsigned d = (unsigned)__cvta_generic_to_shared(dst + r * LD + v * 8);
+        const bf16* g = src + (long long)(r < S ? r : 0) * rs + v * 8;
+        const int bytes = r < S ? 16 : 0;                 // src-size 0: the 16 destination bytes are zero filled
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(g), "r"(bytes) : "memory");
     }
 }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // A fragment of rows [row0, row0+16), k-slice ks of a row-major tile
 template <int LD>
@@ -92,6 +98,7 @@ attn_fwd_kernel(const AttnArgs a) {
     load_tile<HD>(Qs, a.q + (long long)b * a.Sq * a.q_rs + h * HD, a.q_rs, a.Sq, ROWS);
     load_tile<HD>(Ks, a.k + (long long)b * a.Sk * a.k_rs + h * HD, a.k_rs, a.Sk, ROWS);
     load_tile<HD>(Vs, a.v + (long long)b * a.Sk * a.v_rs + h * HD, a.v_rs, a.Sk, ROWS);
+    cp_async_wait_all();
     __syncthreads();
     const int r0 = warp * 16;
     if (r0 >= a.Sq) return;
@@ -212,6 +219,7 @@ attn_bwd_kernel(const AttnArgs a) {
     load_tile<HD>(Vs, a.v + (long long)b * a.Sk * a.v_rs + h * HD, a.v_rs, a.Sk, ROWS);
     load_tile<HD>(dOs, a.d_o + (long long)b * a.Sq * a.o_rs + h * HD, a.o_rs, a.Sq, ROWS);
     for (int i = threadIdx.x; i < ROWS; i += blockDim.x) lse_s[i] = i < a.Sq ? a.lse[(long long)bh * a.Sq + i] : 0.0f;
+    cp_async_wait_all();
     __syncthreads();
     // D_i = dO_i . O_i
     for (int i = warp; i < ROWS; i += 2 * NT) {

@@ -249,15 +249,25 @@ bn_act_bwd_apply_kernel(BnSide a, BnSide r, int res_mode, const __nv_bfloat16* _
 }
 
 // out[k][c] = sum over slabs of part[slab][k][c]
-__global__ void sum_partials_kernel(const float* __restrict__ part, int nslabs, int nacc, int C,
-                                    float* __restrict__ out, int accumulate = 0) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    for (int k = 0; k < nacc; ++k) {
-        float t = 0.0f;
-        for (int b = 0; b < nslabs; ++b) t += part[((long long)b * nacc + k) * C + c];
+// out[k][c] (+)= sum over slabs of part[slab][k][c], fixed order: a CTA owns 32 columns of one accumulator,
+// its 8 warps each sum every 8th slab (coalesced rows), then the warps are added in order.
+__global__ void __launch_bounds__(256)
+sum_partials_kernel(const float* __restrict__ part, int nslabs, int nacc, int C, float* __restrict__ out,
+                    int accumulate = 0) {
+    __shared__ float red[8][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane, k = blockIdx.y;
+    float t = 0.0f;
+    if (c < C)
+        for (int b = wid; b < nslabs; b += 8) t += part[((long long)b * nacc + k) * C + c];
+    red[wid][lane] = t;
+    __syncthreads();
+    if (wid == 0 && c < C) {
+        float r = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) r += red[w][lane];
         float* o = out + (long long)k * C + c;
-        *o = accumulate ? *o + t : t;
+        *o = accumulate ? *o + r : r;
     }
 }
 
@@ -524,7 +534,7 @@ int ew_grid(long long n) {
 
 int slabs_for(long long M, int C) {
     const int colblocks = (C + CR_COLS - 1) / CR_COLS;
-    long long s = (2LL * kNumSMsB200 + colblocks - 1) / colblocks;
+    long long s = (4LL * kNumSMsB200 + colblocks - 1) / colblocks;
     const long long max_by_rows = (M + 31) / 32;
     if (s > max_by_rows) s = max_by_rows;
     if (s < 1) s = 1;
@@ -588,7 +598,7 @@ int eegx_colsum_bf16(const void* y, int64_t ld, int64_t rows, int64_t C, float* 
     float* part = static_cast<float*>(workspace);
     dim3 grid((unsigned)((C + CR_COLS - 1) / CR_COLS), (unsigned)slabs);
     colsum_partial_kernel<<<grid, CR_THREADS, 0, st>>>(static_cast<const __nv_bfloat16*>(y), ld, g, (int)C, part);
-    sum_partials_kernel<<<(int)((C + 127) / 128), 128, 0, st>>>(part, slabs, 1, (int)C, out, accumulate);
+    sum_partials_kernel<<<dim3((unsigned)((C + 31) / 32), 1), 256, 0, st>>>(part, slabs, 1, (int)C, out, accumulate);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
 }
@@ -634,7 +644,7 @@ int eegx_bn_act_bwd_bf16(const void* dout, const void* ya, const float* mean_a, 
     dim3 grid((unsigned)((C + CR_COLS - 1) / CR_COLS), (unsigned)slabs);
     bn_act_bwd_reduce_kernel<<<grid, CR_THREADS, 0, st>>>(a, r, res_mode, static_cast<const __nv_bfloat16*>(dout), g,
                                                           (int)C, dc, part);
-    sum_partials_kernel<<<(int)((C + 127) / 128), 128, 0, st>>>(part, slabs, 3, (int)C, sums);
+    sum_partials_kernel<<<dim3((unsigned)((C + 31) / 32), 3), 256, 0, st>>>(part, slabs, 3, (int)C, sums);
     bn_act_bwd_apply_kernel<<<ew_grid((g.M + 2 * pad) * (C / 2)), 256, 0, st>>>(
         a, r, res_mode, static_cast<const __nv_bfloat16*>(dout), sums, 1.0f / (float)((double)B * (double)T), train,
         static_cast<__nv_bfloat16*>(da), static_cast<__nv_bfloat16*>(dr), g, (int)pad, (int)C, dc);
@@ -668,7 +678,7 @@ int eegx_dwconv5_bwd_bf16(const void* dout, const void* x, const float* w, void*
     dim3 grid((unsigned)((C + CR_COLS - 1) / CR_COLS), (unsigned)slabs);
     dwconv5_bwd_weight_kernel<<<grid, CR_THREADS, 0, st>>>(static_cast<const __nv_bfloat16*>(dout),
                                                            static_cast<const __nv_bfloat16*>(x), g, (int)C, part);
-    sum_partials_kernel<<<(int)((C + 127) / 128), 128, 0, st>>>(part, slabs, 6, (int)C, dwdb_scratch);
+    sum_partials_kernel<<<dim3((unsigned)((C + 31) / 32), 6), 256, 0, st>>>(part, slabs, 6, (int)C, dwdb_scratch);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
 }

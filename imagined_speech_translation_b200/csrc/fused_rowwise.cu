@@ -297,16 +297,19 @@ int ew_grid(long long n8) {
     return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
-int ln_grid(long long rows) {
+// forward: one row per warp, as many CTAs as rows allow (memory bound: occupancy matters);
+// backward: capped, every CTA leaves a (2, C) partial for the fixed-order finalize.
+constexpr int LN_BWD_CTAS_PER_SM = 6;
+int ln_grid(long long rows, bool bwd) {
     long long b = (rows + LN_WARPS - 1) / LN_WARPS;
-    const long long cap = (long long)kNumSMsB200 * 2;
+    const long long cap = (long long)kNumSMsB200 * (bwd ? LN_BWD_CTAS_PER_SM : 16);
     return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
 template <int NVEC>
 void launch_ln_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                    long long rows, int C, float eps, int act, DropoutCfg dc, cudaStream_t st) {
-    ln_fwd_kernel<NVEC><<<ln_grid(rows), LN_WARPS * 32, 0, st>>>(
+    ln_fwd_kernel<NVEC><<<ln_grid(rows, false), LN_WARPS * 32, 0, st>>>(
         static_cast<const __nv_bfloat16*>(x), gamma, beta, static_cast<__nv_bfloat16*>(y), mean, rstd, rows, C, eps,
         act, dc);
 }
@@ -354,7 +357,7 @@ int eegx_layernorm_fwd_bf16(const void* x, const float* gamma, const float* beta
 }
 
 size_t eegx_layernorm_bwd_workspace_bytes(int64_t C) {
-    return (size_t)kNumSMsB200 * 2 * 2 * (size_t)C * sizeof(float);
+    return (size_t)kNumSMsB200 * LN_BWD_CTAS_PER_SM * 2 * (size_t)C * sizeof(float);
 }
 
 int eegx_layernorm_bwd_bf16(const void* dy, const void* x, const float* gamma, const float* beta,
@@ -372,7 +375,7 @@ int eegx_layernorm_bwd_bf16(const void* dy, const void* x, const float* gamma, c
                      eegx::aligned16(beta), EEGX_ERR_ALIGN, "layernorm bwd: pointers must be 16-byte aligned");
     const DropoutCfg dc{reinterpret_cast<const unsigned long long*>(rng_state), site, p};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int grid = ln_grid(rows);
+    const int grid = ln_grid(rows, true);
     float* part = static_cast<float*>(workspace);
     const int nvec = (int)((C + 255) / 256);
     switch (nvec) {

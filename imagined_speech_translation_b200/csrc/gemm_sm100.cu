@@ -42,6 +42,8 @@ struct GemmParams {
     int epilogue;      // 0 none, 1 bias, 2 bias + gelu
     int accumulate;    // D += result (fp32 or bf16 read-modify-write)
     float alpha;
+    int vec_ok;        // D rows are 16-byte addressable: coalesced 128-bit epilogue stores
+    int debug;         // EEGX_GEMM_DEBUG (profiling experiments only): 1 = skip the global stores, 2 = skip the whole epilogue body
 };
 
 // ------------------------------------------------------------------ PTX helpers
@@ -104,8 +106,10 @@ __device__ __forceinline__ void umma_commit(unsigned bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
-    unsigned r[32];
+// TMEM -> registers, 32 lanes x 32 columns.  The load is asynchronous: `tmem_ld32_issue` only starts it
+// and `tmem_ld_wait` (which names the registers as in/out operands, so that no use can be scheduled in
+// front of it) completes it -- this lets the epilogue fetch chunk c+1 while it converts and stores chunk c.
+__device__ __forceinline__ void tmem_ld32_issue(unsigned taddr, unsigned (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
@@ -115,9 +119,15 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
           "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait(unsigned (&r)[32]) {
+    asm volatile(
+        "tcgen05.wait::ld.sync.aligned;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+          "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+          "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+          "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+        :: "memory");
 }
 
 // Shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor, version 1).
@@ -136,69 +146,166 @@ __device__ __forceinline__ unsigned long long make_smem_desc(unsigned saddr, uns
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-// Epilogue of one accumulator tile for the 32 rows a warp owns: TMEM -> registers, alpha / bias /
-// GELU / accumulate, convert, 128-bit stores.  `row` is this lane's output row, n_base the tile's first column.
-template <int BLOCK_N>
-__device__ __forceinline__ void epilogue_rows(const GemmParams& p, unsigned taddr, long long row, long long n_base,
-                                              long long bi) {
-    const bool row_ok = row < p.M;
-    #pragma unroll 1
-                for (int c = 0; c < BLOCK_N / 32; ++c) {
-                    float v[32];
-                    tmem_ld32(taddr + c * 32, v);
-                    const long long col0 = n_base + c * 32;
-                    if (row_ok && col0 < p.N) {
-                        const bool full = col0 + 32 <= p.N;
-    #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
-                        if (p.epilogue >= 1) {
-    #pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (full || col0 + i < p.N) v[i] += __ldg(p.bias + col0 + i);
-                        }
-                        if (p.epilogue == 2) {
-    #pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-                        }
-                        const long long off = bi * p.stride_d + row * p.ldd + col0;
-                        if (p.out_f32) {
-                            float* d = reinterpret_cast<float*>(p.D) + off;
-                            if (full && (p.ldd & 3) == 0) {
-    #pragma unroll
-                                for (int i = 0; i < 32; i += 4) {
-                                    float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                                    if (p.accumulate) {
-                                        const float4 old = *reinterpret_cast<const float4*>(d + i);
-                                        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                                    }
-                                    *reinterpret_cast<float4*>(d + i) = o;
-                                }
-                            } else {
-                                for (int i = 0; i < 32; ++i)
-                                    if (col0 + i < p.N) d[i] = p.accumulate ? d[i] + v[i] : v[i];
-                            }
-                        } else {
-                            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + off;
-                            if (full && (p.ldd & 7) == 0 && !p.accumulate) {
-    #pragma unroll
-                                for (int i = 0; i < 32; i += 8) {
-                                    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i], v[i + 1]);
-                                    __nv_bfloat162 h1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
-                                    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]);
-                                    __nv_bfloat162 h3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
-                                    uint4 o;
-                                    o.x = *reinterpret_cast<unsigned*>(&h0); o.y = *reinterpret_cast<unsigned*>(&h1);
-                                    o.z = *reinterpret_cast<unsigned*>(&h2); o.w = *reinterpret_cast<unsigned*>(&h3);
-                                    *reinterpret_cast<uint4*>(d + i) = o;
-                                }
-                            } else {
-                                for (int i = 0; i < 32; ++i)
-                                    if (col0 + i < p.N)
-                                        d[i] = __float2bfloat16(p.accumulate ? __bfloat162float(d[i]) + v[i] : v[i]);
-                            }
-                        }
+// ---------------------------------------------------------------------------------------- epilogue
+// A warp owns 32 accumulator rows (one per lane in TMEM).  Writing them straight from that layout
+// makes every store instruction touch 32 different cache lines, and measured on the B200 this -- not
+// the tensor pipe -- bounded the K = 768 encoder GEMMs (9472 x 3072 x 768: 47 us with the stores,
+// 31.6 us without).  So the tile is transposed through a small per-warp shared-memory patch
+// (32 rows x 128 bytes, 16-byte row padding: conflict free both ways) and leaves as full 128-byte row
+// segments: 4 lines per store instruction instead of 32.  TMEM reads are double buffered (the load
+// of chunk c+1 is in flight while chunk c is converted).
+constexpr int EPI_ROW_BYTES = 144;                       // 128 data + 16 pad
+constexpr int EPI_WARP_BYTES = 32 * EPI_ROW_BYTES;       // 4608
+constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_WARP_BYTES;
+
+// alpha / bias / GELU on one 32-column chunk of this lane's row
+__device__ __forceinline__ void epilogue_math(const GemmParams& p, const unsigned (&r)[32], float (&v)[32], long long col0) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+    if (p.epilogue >= 1) {
+        if (col0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+                v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N) v[i] += __ldg(p.bias + col0 + i);
+        }
+    }
+    if (p.epilogue == 2) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+    }
+}
+
+// scalar fallback: this lane writes its own row (unaligned D / ragged N)
+__device__ __forceinline__ void epilogue_store_direct(const GemmParams& p, const float (&v)[32], bool row_ok, long long row,
+                                                      long long col0, long long bi) {
+    if (!row_ok || col0 >= p.N) return;
+    const long long off = bi * p.stride_d + row * p.ldd + col0;
+    if (p.out_f32) {
+        float* d = reinterpret_cast<float*>(p.D) + off;
+        for (int i = 0; i < 32; ++i)
+            if (col0 + i < p.N) d[i] = p.accumulate ? d[i] + v[i] : v[i];
+    } else {
+        __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + off;
+        for (int i = 0; i < 32; ++i)
+            if (col0 + i < p.N) d[i] = __float2bfloat16(p.accumulate ? __bfloat162float(d[i]) + v[i] : v[i]);
+    }
+}
+
+__device__ __forceinline__ unsigned pack_bf16(float lo, float hi) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const unsigned*>(&h);
+}
+
+// this lane's 32 values -> its row of the patch, at byte offset `boff` (0 or 64 for bf16, 0 for fp32)
+__device__ __forceinline__ void patch_write(unsigned char* patch, int lane, int boff, const float (&v)[32], bool f32) {
+    uint4* dst = reinterpret_cast<uint4*>(patch + lane * EPI_ROW_BYTES + boff);
+    if (f32) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            dst[i] = make_uint4(__float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]), __float_as_uint(v[4 * i + 2]),
+                                __float_as_uint(v[4 * i + 3]));
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            dst[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
+                                pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+    }
+}
+
+// the patch (32 rows x 128 bytes) -> global: 8 lanes write one row's 128 bytes, 4 rows per instruction
+__device__ __forceinline__ void patch_flush(const GemmParams& p, const unsigned char* patch, int lane, long long row0,
+                                            long long col0, long long bi) {
+    const int piece = lane & 7;
+    const int epp = p.out_f32 ? 4 : 8;                   // elements per 16-byte piece
+    const long long col = col0 + piece * epp;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int r = 4 * it + (lane >> 3);
+        const long long row = row0 + r;
+        if (row < p.M && col < p.N) {
+            uint4 val = *reinterpret_cast<const uint4*>(patch + r * EPI_ROW_BYTES + piece * 16);
+            const long long off = bi * p.stride_d + row * p.ldd + col;
+            if (p.out_f32) {
+                float4* g = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.D) + off);
+                if (p.accumulate) {
+                    const float4 old = *g;
+                    val.x = __float_as_uint(__uint_as_float(val.x) + old.x);
+                    val.y = __float_as_uint(__uint_as_float(val.y) + old.y);
+                    val.z = __float_as_uint(__uint_as_float(val.z) + old.z);
+                    val.w = __float_as_uint(__uint_as_float(val.w) + old.w);
+                }
+                *reinterpret_cast<uint4*>(g) = val;
+            } else {
+                uint4* g = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.D) + off);
+                if (p.accumulate) {
+                    const uint4 old = *g;
+                    const unsigned* o = &old.x;
+                    unsigned* w = &val.x;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+                        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o[k]));
+                        w[k] = pack_bf16(a.x + b.x, a.y + b.y);
                     }
                 }
+                *g = val;
+            }
+        }
+    }
+}
+
+// Epilogue of one accumulator tile for the 32 rows starting at row0 that this warp owns.
+template <int BLOCK_N>
+__device__ __forceinline__ void epilogue_rows(const GemmParams& p, unsigned taddr, long long row0, int lane, long long n_base,
+                                              long long bi, unsigned char* patch) {
+    constexpr int NC = BLOCK_N / 32;
+    static_assert(NC % 2 == 0, "BLOCK_N must be a multiple of 64");
+    if (p.debug == 2) return;
+    const long long row = row0 + lane;
+    const bool row_ok = row < p.M;
+    const bool f32 = p.out_f32 != 0;
+    unsigned r0[32], r1[32];
+    float v[32];
+    tmem_ld32_issue(taddr, r0);
+    tmem_ld_wait(r0);
+#pragma unroll 1
+    for (int c = 0; c < NC; c += 2) {
+        tmem_ld32_issue(taddr + (c + 1) * 32, r1);
+        const long long col0 = n_base + c * 32;
+        epilogue_math(p, r0, v, col0);
+        if (p.debug != 1) {
+            if (!p.vec_ok) {
+                epilogue_store_direct(p, v, row_ok, row, col0, bi);
+            } else {
+                patch_write(patch, lane, 0, v, f32);
+                if (f32) {
+                    __syncwarp();
+                    patch_flush(p, patch, lane, row0, col0, bi);
+                    __syncwarp();
+                }
+            }
+        }
+        tmem_ld_wait(r1);
+        if (c + 2 < NC) tmem_ld32_issue(taddr + (c + 2) * 32, r0);
+        epilogue_math(p, r1, v, col0 + 32);
+        if (p.debug != 1) {
+            if (!p.vec_ok) {
+                epilogue_store_direct(p, v, row_ok, row, col0 + 32, bi);
+            } else {
+                patch_write(patch, lane, f32 ? 0 : 64, v, f32);
+                __syncwarp();
+                patch_flush(p, patch, lane, row0, f32 ? col0 + 32 : col0, bi);
+                __syncwarp();
+            }
+        }
+        if (c + 2 < NC) tmem_ld_wait(r0);
+    }
 }
 
 template <int BLOCK_N, int STAGES>
@@ -208,7 +315,8 @@ struct SmemLayout {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
     static constexpr int NUM_BARS = 2 * STAGES + 4;
-    static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;  // + tmem ptr + alignment slack
+    static constexpr int EPI_OFFSET = BAR_OFFSET + NUM_BARS * 8 + 16;     // per-warp epilogue transpose patches
+    static constexpr int TOTAL = EPI_OFFSET + EPI_BYTES + 1024;          // + alignment slack
 };
 
 template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
@@ -339,9 +447,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int n_blk = (int)(rem / m_blocks), m_blk = (int)(rem % m_blocks);
             mbar_wait(tmem_full_bar(acc), acc_phase);
             tc_fence_after();
-            const long long row = (long long)m_blk * BLOCK_M + quarter * 32 + lane;
+            const long long row0 = (long long)m_blk * BLOCK_M + quarter * 32;
             const unsigned taddr = tmem_base + acc * BLOCK_N + ((unsigned)(quarter * 32) << 16);
-            epilogue_rows<BLOCK_N>(p, taddr, row, (long long)n_blk * BLOCK_N, bi);
+            epilogue_rows<BLOCK_N>(p, taddr, row0, lane, (long long)n_blk * BLOCK_N, bi,
+                                   smem + L::EPI_OFFSET + (warp - 2) * EPI_WARP_BYTES);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
@@ -420,7 +529,8 @@ struct SmemLayout2 {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
     static constexpr int NUM_BARS = 2 * STAGES + 4;
-    static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;
+    static constexpr int EPI_OFFSET = BAR_OFFSET + NUM_BARS * 8 + 16;
+    static constexpr int TOTAL = EPI_OFFSET + EPI_BYTES + 1024;
 };
 
 template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
@@ -553,9 +663,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const int n_blk = (int)(rem / m_blocks), m_blk = (int)(rem % m_blocks);
             mbar_wait(tmem_full_bar(acc), acc_phase);
             tc_fence_after();
-            const long long row = (long long)m_blk * 2 * BLOCK_M + (long long)rank * BLOCK_M + quarter * 32 + lane;
+            const long long row0 = (long long)m_blk * 2 * BLOCK_M + (long long)rank * BLOCK_M + quarter * 32;
             const unsigned taddr = tmem_base + acc * BLOCK_N + ((unsigned)(quarter * 32) << 16);
-            epilogue_rows<BLOCK_N>(p, taddr, row, (long long)n_blk * BLOCK_N, bi);
+            epilogue_rows<BLOCK_N>(p, taddr, row0, lane, (long long)n_blk * BLOCK_N, bi,
+                                   smem + L::EPI_OFFSET + (warp - 2) * EPI_WARP_BYTES);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -684,7 +795,7 @@ extern "C" int eegx_gemm_bf16(const eegx_gemm_desc* d, const void* A, const void
     int block_n = 128;
     {
         const int cand[4] = {64, 128, 192, 256};
-        const double eff[4] = {1.7, 1.22, 1.04, 1.0};
+        const double eff[4] = {1.7, 1.35, 1.04, 1.0};
         double best = 1e300;
         for (int i = 0; i < 4; ++i) {
             const int bn = cand[i];
@@ -716,6 +827,12 @@ extern "C" int eegx_gemm_bf16(const eegx_gemm_desc* d, const void* A, const void
     p.bias = bias; p.D = D;
     p.out_f32 = d->out_f32; p.epilogue = d->epilogue; p.accumulate = d->accumulate;
     p.alpha = d->alpha;
+    static const int env_debug = [] { const char* v = getenv("EEGX_GEMM_DEBUG"); return v ? atoi(v) : 0; }();
+    p.debug = env_debug;
+    {
+        const long long es = d->out_f32 ? 4 : 2, epp = 16 / es;
+        p.vec_ok = (d->ldd % epp) == 0 && (d->N % epp) == 0 && (d->batch == 1 || (d->stride_d % epp) == 0);
+    }
 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool am = d->a_mn_major != 0, bm = d->b_mn_major != 0;

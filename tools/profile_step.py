@@ -48,6 +48,41 @@ print(f"B={B}: {ms:.2f} ms/step  {B/ms*1e3:.0f} trials/s  loss {loss.item():.3f}
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     step(); torch.cuda.synchronize()
+if os.environ.get("EEGX_TRACE", "0") == "1":
+    prof.export_chrome_trace(os.path.join("gpurun_out", "step_trace.json"))
+    import json
+    ev = [e for e in json.load(open(os.path.join("gpurun_out", "step_trace.json")))["traceEvents"]
+          if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset") and "dur" in e]
+    ev.sort(key=lambda e: e["ts"])
+    t0 = ev[0]["ts"]; t1 = max(e["ts"] + e["dur"] for e in ev)
+    def union(evs):
+        tot, cur_s, cur_e = 0.0, None, None
+        for e in sorted(evs, key=lambda e: e["ts"]):
+            s_, e_ = e["ts"], e["ts"] + e["dur"]
+            if cur_e is None or s_ > cur_e:
+                if cur_e is not None: tot += cur_e - cur_s
+                cur_s, cur_e = s_, e_
+            else:
+                cur_e = max(cur_e, e_)
+        return tot + (cur_e - cur_s if cur_e is not None else 0.0)
+    gemm = [e for e in ev if "gemm" in e["name"]]
+    attn = [e for e in ev if "attn_" in e["name"]]
+    lines = [f"kernels {len(ev)}  wall {(t1 - t0) / 1e3:.2f} ms  busy(union) {union(ev) / 1e3:.2f} ms  sum {sum(e['dur'] for e in ev) / 1e3:.2f} ms",
+             f"gemm: n {len(gemm)} union {union(gemm) / 1e3:.2f} ms sum {sum(e['dur'] for e in gemm) / 1e3:.2f} ms",
+             f"attn: n {len(attn)} union {union(attn) / 1e3:.2f} ms sum {sum(e['dur'] for e in attn) / 1e3:.2f} ms",
+             f"non-gemm union {union([e for e in ev if 'gemm' not in e['name']]) / 1e3:.2f} ms"]
+    # coarse timeline: 1 ms buckets, fraction busy and fraction with a gemm running
+    nb = int((t1 - t0) / 1000) + 1
+    for b in range(nb):
+        lo, hi = t0 + b * 1000, t0 + (b + 1) * 1000
+        def cover(evs):
+            c = [dict(ts=max(e["ts"], lo), dur=min(e["ts"] + e["dur"], hi) - max(e["ts"], lo)) for e in evs
+                 if e["ts"] < hi and e["ts"] + e["dur"] > lo]
+            return union(c) / 1000 if c else 0.0
+        n_k = sum(1 for e in ev if lo <= e["ts"] < hi)
+        lines.append(f"  ms {b:3d}: busy {cover(ev):.2f} gemm {cover(gemm):.2f} kernels {n_k}")
+    open(os.path.join("gpurun_out", "step_timeline.txt"), "w").write("\n".join(lines))
+    print("\n".join(lines[:4]))
 tab = prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=200)
 os.makedirs("gpurun_out", exist_ok=True)
 open(os.path.join("gpurun_out", f"step_profile_B{B}.txt"), "w").write(tab)
