@@ -299,7 +299,7 @@ int ew_grid(long long n8) {
 
 // forward: one row per warp, as many CTAs as rows allow (memory bound: occupancy matters);
 // backward: capped, every CTA leaves a (2, C) partial for the fixed-order finalize.
-constexpr int LN_BWD_CTAS_PER_SM = 6;
+constexpr int LN_BWD_CTAS_PER_SM = 2;
 int ln_grid(long long rows, bool bwd) {
     long long b = (rows + LN_WARPS - 1) / LN_WARPS;
     const long long cap = (long long)kNumSMsB200 * (bwd ? LN_BWD_CTAS_PER_SM : 16);

@@ -96,8 +96,10 @@ def _f32(p: torch.Tensor) -> torch.Tensor:
 def grad_buffer(p) -> Optional[torch.Tensor]:
     """The parameter's existing gradient buffer if a kernel may accumulate into it in place (fp32,
     contiguous, CUDA) -- the flat buffers of FlatAdamW qualify -- else None (autograd accumulates)."""
-    g = getattr(p, "grad", None)
-    if g is None or not p.is_leaf or g.dtype != torch.float32 or not g.is_cuda or not g.is_contiguous():
+    if p is None or not p.is_leaf:
+        return None
+    g = p.grad
+    if g is None or g.dtype != torch.float32 or not g.is_cuda or not g.is_contiguous():
         return None
     return g
 
