@@ -95,6 +95,9 @@ SIGNATURES.update({
     "eegx_se_scale_fwd_bf16": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64] + _RNG + [_P]),
     "eegx_se_scale_bwd_bf16": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64] + _RNG + [_P]),
     "eegx_nct_to_rows_bf16": (_I, [_P, _I64, _P, _I64, _I64, _I64, _I64, _P]),
+    "eegx_robust_fit_f32": (_I, [_P, _I64, _I64, _F, _F, _P, _P, _P]),
+    "eegx_region_std_f32": (_I, [_P, _I64, _I64, _P, _P]),
+    "eegx_augment_f32": (_I, [_P, _P, _I64, _I64, _I64, _P, _P, _P, _P, _U32, _P]),
     "eegx_ce_fwd_bf16": (_I, [_P, _I64, _P, _I64, _I64, _I64, _P, _P, _P]),
     "eegx_ce_bwd_bf16": (_I, [_P, _I64, _P, _P, _P, _P, _I64, _I64, _I64, _P]),
     "eegx_attn_fwd_bf16": (_I, [C.POINTER(AttnDesc), _P, _P, _P, _P, _P] + _RNG + [_P]),

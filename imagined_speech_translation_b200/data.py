@@ -1,0 +1,188 @@
+"""Data side of the hot path on the B200: the reference ``EEGDataset``
+(``main_model/src/data/dataset.py:18-553``) with the arithmetic moved to the GPU.
+
+``EEGDataset`` keeps the reference constructor and the per-item dict, but the per-trial numpy /
+sklearn work -- nan_to_num, region gather, RobustScaler fit and transform, augmentation -- runs
+batched on the device: ``collate_raw`` hands the trainer one ``(B, 125, T)`` tensor per batch and
+``RegionNormalizer`` / ``augment_regions`` do the rest in a handful of launches.
+No CPU fallback for the arithmetic: ``__getitem__`` returns the *raw* trial plus the token ids.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+from functools import lru_cache
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, fused
+from .preprocess import REGION_ORDER, RegionNormalizer
+
+# Electrode names per region: the reference's montage split (main_model/src/data/utils.py:13-28).
+ELECTRODE_REGIONS = {
+    'frontal': ('FC5', 'F5', 'F7', 'F3', 'FC1', 'F1', 'AF3', 'Fz', 'FC2', 'F2', 'AF4', 'Fp2', 'F4', 'F6', 'F8', 'FC6'),
+    'temporal': ('T9', 'FT9', 'T7', 'TP7', 'FT8', 'T10', 'FT10', 'T8', 'TP8'),
+    'central': ('C5', 'C3', 'FC3', 'C1', 'CP1', 'Cz', 'CP2', 'C2', 'C4', 'FC4', 'C6'),
+    'parietal': ('P7', 'P5', 'CP3', 'P3', 'PO3', 'PO1', 'PO2', 'P4', 'PO4', 'P6', 'CP4', 'P8'),
+}
+DEFAULT_TEXT = "数据样本"      # dataset.py:312, 427
+
+
+def build_region_indices(ch_names: Sequence[str]) -> Dict[str, List[int]]:
+    """Channel rows per region, in montage order (``_build_region_indices``, dataset.py:339-353)."""
+    return {r: [i for i, ch in enumerate(ch_names) if ch in ELECTRODE_REGIONS[r]] for r in REGION_ORDER}
+
+
+# ------------------------------------------------------------------------------------------ augmentation
+def augment_regions(regions: List[torch.Tensor], p_noise: float = 0.3, p_scale: float = 0.2, p_shift: float = 0.15,
+                    generator: Optional[torch.Generator] = None) -> List[torch.Tensor]:
+    """``_augment_eeg_regions`` (dataset.py:227-261) for a batch: per (trial, region) and independently,
+    Gaussian noise of 5 % of the region's std with probability 0.3, an amplitude factor U(0.9, 1.1) with
+    probability 0.2, a circular time shift of -2..2 samples with probability 0.15.  The decisions are drawn
+    per trial on the host RNG ``generator`` (the reference uses numpy's global stream, so parity is
+    distributional), the arithmetic is one fused pass per region."""
+    lib = _lib.lib()
+    out = []
+    for reg in regions:
+        if not reg.is_cuda or reg.dtype != torch.float32:
+            raise _lib.EegxError("augment_regions needs CUDA float32 regions (no CPU fallback)")
+        reg = reg.contiguous()
+        B, C, T = reg.shape
+        u = torch.rand(B, 5, generator=generator)
+        std = torch.empty(B, dtype=torch.float32, device=reg.device)
+        _lib.check(lib.eegx_region_std_f32(_lib.ptr(reg), B, C * T, _lib.ptr(std), _lib.stream_ptr()),
+                   "eegx_region_std_f32")
+        noise_on = (u[:, 0] < p_noise).to(reg.device)
+        sigma = torch.where(noise_on, (std * 0.05).clamp_min(1e-6), torch.zeros_like(std))
+        scale = torch.where(u[:, 1] < p_scale, 0.9 + 0.2 * u[:, 2], torch.ones(B)).to(reg.device)
+        shift = torch.where(u[:, 3] < p_shift, torch.floor(u[:, 4] * 5).to(torch.int32) - 2,
+                            torch.zeros(B, dtype=torch.int32)).to(reg.device)
+        out.append(apply_augmentation(reg, sigma, scale, shift))
+    return out
+
+
+def apply_augmentation(reg: torch.Tensor, sigma: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor) -> torch.Tensor:
+    """out[b, c, t] = scale[b] * (x[b, c, (t - shift[b]) mod T] + sigma[b] * N(0, 1)) -- noise, then scaling,
+    then np.roll, exactly the reference's order."""
+    B, C, T = reg.shape
+    res = torch.empty_like(reg)
+    rng, site = fused.rng_state(reg.device), fused._next_site()
+    _lib.check(_lib.lib().eegx_augment_f32(_lib.ptr(reg), _lib.ptr(res), B, C, T,
+                                           _lib.ptr(sigma.float().contiguous()), _lib.ptr(scale.float().contiguous()),
+                                           _lib.ptr(shift.to(torch.int32).contiguous()), _lib.ptr(rng), site,
+                                           _lib.stream_ptr()), "eegx_augment_f32")
+    return res
+
+
+# ------------------------------------------------------------------------------------------ dataset
+class EEGDataset(torch.utils.data.Dataset):
+    """Same constructor as the reference (dataset.py:23-24).  ``ds[i]`` returns
+    ``{'raw': (125, T) float32, 'decoder_input_ids', 'labels', 'attention_mask'}``; ``collate_raw`` stacks
+    a batch; ``normalizer()`` is the GPU ``RegionNormalizer`` fitted the reference's way (a random subset
+    of min(100, max(10, N // 10)) samples, RobustScaler(5, 95)); ``to_regions(batch)`` yields the list of
+    four ``(B, C_r, T)`` tensors the reference's ``ds[i]['eeg']`` holds (augmented if enabled)."""
+
+    def __init__(self, data_dir, csv_path, tokenizer, max_length=64, eps=1e-6, max_samples=None,
+                 data_augmentation=True, precompute_stats=False, device="cuda"):
+        import pandas as pd
+        self.tokenizer = tokenizer
+        self.max_length = max_length
+        self.eps = eps
+        self.max_samples = max_samples
+        self.data_augmentation = data_augmentation
+        self.precompute_stats = precompute_stats
+        self.device = torch.device(device)
+        self.vocab_size = len(tokenizer.get_vocab())
+        self.ch_names = pd.read_csv(csv_path)['label'].to_numpy()
+        self.region_indices = build_region_indices(self.ch_names)
+        self.region_channel_counts = {r: len(ix) for r, ix in self.region_indices.items()}
+        for r, ix in self.region_indices.items():
+            if not ix:
+                raise ValueError(f"No channels found for {r} region!")
+        if self.tokenizer.pad_token is None:                      # _setup_tokenizer_safe (dataset.py:365-385)
+            self.tokenizer.pad_token = self.tokenizer.eos_token
+        if not os.path.exists(data_dir):
+            raise FileNotFoundError(f"Data directory not found: {data_dir}")
+        self.data_files = [os.path.join(data_dir, f) for f in os.listdir(data_dir) if f.endswith('.pkl')]
+        if not self.data_files:
+            raise ValueError(f"No .pkl files found in {data_dir}")
+        self.sample_index = self._build_sample_index()
+        self._normalizer = None
+        self._load_file = lru_cache(maxsize=32)(self._load_file_uncached)
+
+    # -- indexing / loading (dataset.py:71-100, 153-170) ------------------------------------------------
+    def _build_sample_index(self):
+        index = []
+        for path in self.data_files:
+            with open(path, 'rb') as fh:
+                loaded = pickle.load(fh)
+            n = len(loaded) if isinstance(loaded, list) else 1
+            for i in range(n):
+                index.append({'file': path, 'index': i})
+                if self.max_samples and len(index) >= self.max_samples:
+                    return index
+        return index
+
+    @staticmethod
+    def _load_file_uncached(path):
+        with open(path, 'rb') as fh:
+            loaded = pickle.load(fh)
+        return loaded if isinstance(loaded, list) else [loaded]
+
+    def _raw(self, idx) -> Optional[dict]:
+        info = self.sample_index[idx]
+        sample = self._load_file(info['file'])[info['index']]
+        if not isinstance(sample, dict) or 'input_features' not in sample or 'text' not in sample:
+            return None
+        arr = np.asarray(sample['input_features'], dtype=np.float32)
+        if arr.ndim < 2 or arr.shape[1] != len(self.ch_names):      # _validate_sample: (1, 125, T)
+            return None
+        return {'eeg': arr.squeeze(), 'text': sample.get('text', '')}
+
+    def __len__(self):
+        return len(self.sample_index)
+
+    # -- tokenisation (dataset.py:422-494) ----------------------------------------------------------------
+    def _safe_tokenize(self, text):
+        if not text or not isinstance(text, str) or not text.strip():
+            text = DEFAULT_TEXT
+        enc = self.tokenizer(text.strip(), max_length=self.max_length, padding='max_length', truncation=True,
+                             return_tensors='pt', add_special_tokens=True)
+        input_ids = enc['input_ids'].squeeze(0).clamp(0, self.vocab_size - 1)
+        start = self.tokenizer.bos_token_id
+        if start is None:
+            start = self.tokenizer.eos_token_id
+        if start is None or start >= self.vocab_size:
+            start = self.tokenizer.pad_token_id
+        decoder_input_ids = torch.cat([torch.tensor([start]), input_ids[:-1]]).clamp(0, self.vocab_size - 1)
+        labels = input_ids.clone()
+        labels[input_ids == self.tokenizer.pad_token_id] = -100
+        return {'decoder_input_ids': decoder_input_ids, 'labels': labels,
+                'attention_mask': enc['attention_mask'].squeeze(0)}
+
+    def __getitem__(self, idx):
+        raw = self._raw(idx)
+        if raw is None:
+            raise ValueError(f"sample {idx} is malformed (the reference silently substitutes zeros here)")
+        return {'raw': torch.from_numpy(np.ascontiguousarray(raw['eeg'])), **self._safe_tokenize(raw['text'])}
+
+    @staticmethod
+    def collate_raw(items):
+        return {k: torch.stack([it[k] for it in items]) for k in items[0]}
+
+    # -- GPU normalisation / augmentation -----------------------------------------------------------------
+    def normalizer(self) -> RegionNormalizer:
+        if self._normalizer is None:
+            n_all = len(self.sample_index)
+            size = min(min(100, max(10, n_all // 10)), n_all)       # dataset.py:105-108
+            chosen = np.random.choice(n_all, size=size, replace=False)
+            fit = [self._raw(int(i)) for i in chosen]
+            fit = torch.from_numpy(np.stack([f['eeg'] for f in fit if f is not None]))
+            self._normalizer = RegionNormalizer.fit(fit, self.region_indices, device=self.device)
+        return self._normalizer
+
+    def to_regions(self, batch, generator: Optional[torch.Generator] = None) -> List[torch.Tensor]:
+        regions = self.normalizer()(batch['raw'].to(self.device, non_blocking=True).float())
+        return augment_regions(regions, generator=generator) if self.data_augmentation else regions

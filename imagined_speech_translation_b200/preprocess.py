@@ -200,6 +200,40 @@ class RegionNormalizer:
         scales = {n: s.scale_ for n, s in dataset.scalers.items()}
         return cls(dataset.region_indices, centers, scales, device=device)
 
+    @classmethod
+    def fit(cls, samples: torch.Tensor, region_indices: Dict[str, Sequence[int]],
+            quantile_range=(5.0, 95.0), device="cuda"):
+        """The scaler fit of ``EEGDataset._initialize_scalers_efficiently`` (dataset.py:102-151) on the
+        GPU: ``samples`` (n, C_in, T) float32 -- the fit subset, already chosen by the caller -- are
+        nan_to_num'ed and gathered per region, every channel's n*T values go through an exact radix
+        select for the median and the two percentiles (``RobustScaler.center_`` / ``scale_``)."""
+        samples = torch.as_tensor(samples, dtype=torch.float32, device=device)
+        if samples.dim() == 4 and samples.shape[1] == 1:          # pickled as (1, C, T)
+            samples = samples[:, 0]
+        _require_cuda_f32(samples, "samples", 3)
+        n, _, T = samples.shape
+        centers, scales = {}, {}
+        lib = _lib.lib()
+        for name in REGION_ORDER:
+            idx = torch.as_tensor(np.asarray(region_indices[name], dtype=np.int32), device=samples.device)
+            reg = normalize_dense(samples.contiguous(), idx, None, None)          # gather + nan_to_num
+            rows = reg.permute(1, 0, 2).reshape(idx.numel(), n * T).contiguous()   # channel-major, time-concatenated
+            cen = torch.empty(idx.numel(), dtype=torch.float32, device=samples.device)
+            sca = torch.empty_like(cen)
+            _lib.check(lib.eegx_robust_fit_f32(_lib.ptr(rows), idx.numel(), n * T, float(quantile_range[0]),
+                                               float(quantile_range[1]), _lib.ptr(cen), _lib.ptr(sca),
+                                               _lib.stream_ptr()), "eegx_robust_fit_f32")
+            centers[name], scales[name] = cen.cpu().numpy(), sca.cpu().numpy()
+        return cls(region_indices, centers, scales, device=device)
+
+    @property
+    def centers(self):
+        return {n: self._center[n] for n in self._robust_names}
+
+    @property
+    def scales(self):
+        return {n: self._scale[n] for n in self._robust_names}
+
     def _layout(self, names, B, T):
         key = (tuple(names), B, T)
         hit = self._plan_cache.get(key)

@@ -291,6 +291,28 @@ int eegx_ce_fwd_bf16(const void* logits, int64_t ld, const int64_t* labels, int6
 int eegx_ce_bwd_bf16(const void* logits, int64_t ld, const int64_t* labels, const float* lse, const float* coef,
                      void* dlogits, int64_t rows, int64_t V, int64_t ignore_index, void* stream);
 
+
+/* ------------------------------------------------------------------------
+ * Data-side rows of the path that the reference runs in numpy / sklearn on the host.
+ *
+ * eegx_robust_fit_f32: RobustScaler(quantile_range=(q_lo, q_hi)).fit of
+ *   EEGDataset._initialize_scalers_efficiently (main_model/src/data/dataset.py:102-151).
+ *   x: (C, n) fp32, row c = every fit sample of channel c concatenated over time (nan_to_num applied).
+ *   center[c] = median, scale[c] = P(q_hi) - P(q_lo) with numpy's linear-interpolated percentiles, zero
+ *   scales replaced by 1.  Exact (radix select), deterministic.
+ * eegx_region_std_f32: population standard deviation of each row of a (B, n) matrix (np.std of a whole
+ *   region, dataset.py:240).
+ * eegx_augment_f32: EEGDataset._augment_eeg_regions (dataset.py:227-261) for a batch of one region:
+ *   out[b, c, t] = scale[b] * (x[b, c, (t - shift[b]) mod T] + sigma[b] * N(0, 1)); sigma[b] = 0 disables the
+ *   noise, scale[b] = 1 the scaling, shift[b] = 0 the roll (the caller draws the per-trial decisions).
+ *   Noise: Philox(seed, step, site, source index) + Box-Muller.  out must not alias x.
+ * ------------------------------------------------------------------------ */
+int eegx_robust_fit_f32(const float* x, int64_t C, int64_t n, float q_lo, float q_hi, float* center, float* scale,
+                        void* stream);
+int eegx_region_std_f32(const float* x, int64_t B, int64_t n, float* out, void* stream);
+int eegx_augment_f32(const float* x, float* out, int64_t B, int64_t C, int64_t T, const float* sigma,
+                     const float* scale, const int32_t* shift, const uint64_t* rng_state, uint32_t site, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
