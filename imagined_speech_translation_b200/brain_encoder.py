@@ -7,6 +7,8 @@ the tcgen05 GEMM.  ``forward(list[4] of (B, C_r, T) CUDA tensors) -> (B, hidden_
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -16,6 +18,7 @@ from .layers import Conv1DWithAttention, _layer_norm, _mha, run_sequential
 from .nn_ops import PAD
 
 REGION_NAMES = ['frontal', 'temporal', 'central', 'parietal']
+_REGION_STREAMS = int(os.environ.get("EEGX_REGION_STREAMS", "4"))   # concurrent region encoders (1..4)
 
 
 class BrainRegionEncoder(nn.Module):
@@ -99,13 +102,16 @@ class BrainRegionEncoder(nn.Module):
         if not getattr(self, "parallel_regions", True):
             return [self.region_encoders[n](eeg_data[i]) for i, n in enumerate(self.region_names)]
         cur = torch.cuda.current_stream()
-        if getattr(self, "_streams", None) is None or self._streams[0].device != eeg_data[0].device:
-            self._streams = [torch.cuda.Stream(device=eeg_data[0].device) for _ in self.region_names]
+        n_streams = max(1, min(len(self.region_names), int(getattr(self, "region_streams", _REGION_STREAMS))))
+        if getattr(self, "_streams", None) is None or len(self._streams) != n_streams or \
+                self._streams[0].device != eeg_data[0].device:
+            self._streams = [torch.cuda.Stream(device=eeg_data[0].device) for _ in range(n_streams)]
         start = cur.record_event()
         feats = []
-        for i, name in enumerate(self.region_names):
-            s = self._streams[i]
+        for s in self._streams:
             s.wait_event(start)
+        for i, name in enumerate(self.region_names):
+            s = self._streams[i % n_streams]
             with torch.cuda.stream(s):
                 eeg_data[i].record_stream(s)
                 f = self.region_encoders[name](eeg_data[i])

@@ -33,20 +33,29 @@ class FlatAdamW(torch.optim.Optimizer):
 
     # ------------------------------------------------------------------ flat buffers
     def _build(self):
-        flats = []
+        """One contiguous fp32 gradient buffer for ALL groups (a single all-reduce covers it) and one
+        parameter / moment buffer per group (the groups differ in learning rate)."""
+        plan = []
         for group in self.param_groups:
             ps = [p for p in group['params'] if p.grad is not None]
-            if not ps:
-                flats.append(None)
-                continue
-            dev = ps[0].device
             for p in ps:
                 if p.dtype != torch.float32 or not p.is_cuda:
                     raise _lib.EegxError("FlatAdamW needs float32 CUDA parameters (no CPU fallback)")
             sizes = [(p.numel() + 3) // 4 * 4 for p in ps]          # keep every view 16-byte aligned
+            plan.append((ps, sizes))
+        if not any(ps for ps, _ in plan):
+            raise _lib.EegxError("FlatAdamW.step() called before any backward pass")
+        dev = next(ps[0].device for ps, _ in plan if ps)
+        self._all_grads = torch.zeros(sum(sum(sz) for _, sz in plan), device=dev)
+        flats, base = [], 0
+        for ps, sizes in plan:
+            if not ps:
+                flats.append(None)
+                continue
             total = sum(sizes)
             flat_p = torch.zeros(total, device=dev)
-            flat_g = torch.zeros(total, device=dev)
+            flat_g = self._all_grads[base:base + total]
+            base += total
             off = 0
             for p, n in zip(ps, sizes):
                 k = p.numel()
@@ -58,7 +67,6 @@ class FlatAdamW(torch.optim.Optimizer):
             flats.append(dict(p=flat_p, g=flat_g, m=torch.zeros_like(flat_p), v=torch.zeros_like(flat_p),
                               params=ps))
         self._flat = flats
-        dev = next(f for f in flats if f is not None)['p'].device
         self._norm_sq = torch.zeros(1, device=dev)
         self._ws = torch.empty(_lib.lib().eegx_sumsq_workspace_bytes(), dtype=torch.uint8, device=dev)
 
@@ -67,14 +75,12 @@ class FlatAdamW(torch.optim.Optimizer):
         all-reduce runs directly on these."""
         if self._flat is None:
             self._build()
-        return [f['g'] for f in self._flat if f is not None]
+        return [self._all_grads]
 
     def zero_grad(self, set_to_none: bool = False):
         if self._flat is None:
             return super().zero_grad(set_to_none=True)
-        for f in self._flat:
-            if f is not None:
-                f['g'].zero_()
+        self._all_grads.zero_()
 
     # ------------------------------------------------------------------ step
     @torch.no_grad()
