@@ -60,7 +60,7 @@ SIGNATURES["eegx_sumsq_f32"] = (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c
                                           C.c_size_t, C.c_void_p])
 SIGNATURES["eegx_adamw_clip_f32"] = (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                                C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
-                                               C.c_int64, C.c_void_p, C.c_float, C.c_float, C.c_void_p])
+                                               C.c_int64, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p])
 
 
 class AttnDesc(C.Structure):

@@ -8,6 +8,8 @@
 // AdamW follows torch.optim.AdamW (decoupled decay applied first, eps added after the bias-
 // corrected sqrt); the reference's transformers.AdamW is removed upstream.
 // Algorithmic bytes per parameter: 4 (grad-norm read) + 16 read + 12 written.
+#include <cuda_bf16.h>
+
 #include "eegx_common.h"
 
 namespace {
@@ -56,7 +58,7 @@ __global__ void sumsq_final_kernel(const double* __restrict__ partials, int coun
 __global__ void __launch_bounds__(NT)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              long long n, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt,
-             const float* __restrict__ norm_sq, float max_norm, float grad_scale) {
+             const float* __restrict__ norm_sq, float max_norm, float grad_scale, __nv_bfloat16* __restrict__ w16) {
     // clip coefficient of clip_grad_norm_: min(1, max_norm / (||g|| + 1e-6)); grads may carry a
     // constant factor (grad_scale, e.g. 1/world_size) that is folded in here.
     float coef = grad_scale;
@@ -86,9 +88,19 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
         upd(pp.x, gg.x, mm.x, vv.x); upd(pp.y, gg.y, mm.y, vv.y);
         upd(pp.z, gg.z, mm.z, vv.z); upd(pp.w, gg.w, mm.w, vv.w);
         p4[i] = pp; m4[i] = mm; v4[i] = vv;
+        if (w16 != nullptr) {          // bf16 shadow of the updated weights: what the GEMMs read next step
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(pp.x, pp.y), hi = __floats2bfloat162_rn(pp.z, pp.w);
+            uint2 o;
+            o.x = *reinterpret_cast<const unsigned*>(&lo);
+            o.y = *reinterpret_cast<const unsigned*>(&hi);
+            reinterpret_cast<uint2*>(w16)[i] = o;
+        }
     }
     if (blockIdx.x == 0)
-        for (long long i = (n4 << 2) + threadIdx.x; i < n; i += NT) upd(p[i], g[i], m[i], v[i]);
+        for (long long i = (n4 << 2) + threadIdx.x; i < n; i += NT) {
+            upd(p[i], g[i], m[i], v[i]);
+            if (w16 != nullptr) w16[i] = __float2bfloat16(p[i]);
+        }
 }
 
 }  // namespace
@@ -115,7 +127,8 @@ extern "C" int eegx_sumsq_f32(const float* g, int64_t n, float* out, int accumul
 
 extern "C" int eegx_adamw_clip_f32(float* p, const float* g, float* m, float* v, int64_t n, float lr,
                                    float beta1, float beta2, float eps, float weight_decay, int64_t step,
-                                   const float* grad_norm_sq, float max_norm, float grad_scale, void* stream) {
+                                   const float* grad_norm_sq, float max_norm, float grad_scale, void* w16,
+                                   void* stream) {
     if (int rc = eegx::require_sm100()) return rc;
     EEGX_REQUIRE(n >= 0 && step >= 1, EEGX_ERR_ARG, "bad n/step");
     if (n == 0) return EEGX_OK;
@@ -128,7 +141,8 @@ extern "C" int eegx_adamw_clip_f32(float* p, const float* g, float* m, float* v,
     if (blocks < 1) blocks = 1;
     if (blocks > eegx::kNumSMsB200 * 8) blocks = eegx::kNumSMsB200 * 8;
     adamw_kernel<<<(int)blocks, NT, 0, static_cast<cudaStream_t>(stream)>>>(
-        p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, grad_norm_sq, max_norm, grad_scale);
+        p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, grad_norm_sq, max_norm, grad_scale,
+        static_cast<__nv_bfloat16*>(w16));
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
 }

@@ -8,6 +8,7 @@ bf16 once per optimizer step (cache keyed on the parameter's version counter).
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -17,6 +18,7 @@ from . import fused, ops
 PAD = 4   # largest Conv1d padding in the encoder (kernel 9, layers.py:30)
 
 _pack_cache: dict = {}
+_USE_SHADOW = os.environ.get("EEGX_BF16_SHADOW", "1") != "0"     # A/B switch for the AdamW-written bf16 weight shadows
 
 
 def _cached(param: torch.Tensor, tag: str, make):
@@ -39,21 +41,32 @@ def clear_pack_cache():
     _pack_cache.clear()
 
 
+def _bf16_src(p: torch.Tensor) -> torch.Tensor:
+    """bf16 values of a parameter (or of a row-slice view of one): the shadow the fused AdamW kernel keeps
+    beside the fp32 master when it is current (no cast kernel), else a cast."""
+    base = p._base if p._base is not None else p
+    sh = getattr(base, "_eegx_w16", None) if _USE_SHADOW else None
+    if sh is not None and getattr(base, "_eegx_w16_ver", -1) == base._version and sh.shape == base.shape:
+        if p is base:
+            return sh
+        return sh.as_strided(p.shape, p.stride(), sh.storage_offset() + p.storage_offset() - base.storage_offset())
+    return p.detach().to(torch.bfloat16)
+
+
 def _w_linear(w):            # (N, K) fp32 -> bf16, rows zero-padded to a multiple of 8 (TMA row pitch of dy)
-    def make(p):
-        n_pad = (-p.shape[0]) % 8
-        p16 = p.to(torch.bfloat16)
+    def make(_):
+        p16 = _bf16_src(w)
+        n_pad = (-p16.shape[0]) % 8
         return (torch.nn.functional.pad(p16, (0, 0, 0, n_pad)) if n_pad else p16).contiguous()
     return _cached(w, "lin", make)
 
 
 def _w_conv_fwd(w):          # (Cout, Cin, k) -> (Cout, k*Cin) bf16, K index = tap*Cin + ci
-    return _cached(w, "convf", lambda p: p.permute(0, 2, 1).reshape(p.shape[0], -1).to(torch.bfloat16).contiguous())
+    return _cached(w, "convf", lambda _: _bf16_src(w).permute(0, 2, 1).reshape(w.shape[0], -1).contiguous())
 
 
 def _w_conv_dgrad(w):        # (Cout, Cin, k) -> (k*Cout, Cin) bf16 with taps flipped (K x N, N contiguous)
-    return _cached(w, "convd", lambda p: p.flip(2).permute(2, 0, 1).reshape(-1, p.shape[1]).to(torch.bfloat16).contiguous())
-
+    return _cached(w, "convd", lambda _: _bf16_src(w).flip(2).permute(2, 0, 1).reshape(-1, w.shape[1]).contiguous())
 
 
 def _wgrad(dy: torch.Tensor, x: torch.Tensor, into: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
@@ -214,7 +227,7 @@ def conv1d_cl(buf: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tens
 def _w_cat(ws):
     """bf16 pack of several (N_i, K) weights stacked along N (cached on the first weight's version)."""
     tag = "cat:" + ",".join(str(id(w)) for w in ws[1:])
-    return _cached(ws[0], tag, lambda p: torch.cat([p] + [w.detach() for w in ws[1:]], 0).to(torch.bfloat16).contiguous())
+    return _cached(ws[0], tag, lambda _: torch.cat([_bf16_src(w) for w in ws], 0).contiguous())
 
 
 class _LinearCat(torch.autograd.Function):

@@ -41,7 +41,7 @@ class FlatAdamW(torch.optim.Optimizer):
             for p in ps:
                 if p.dtype != torch.float32 or not p.is_cuda:
                     raise _lib.EegxError("FlatAdamW needs float32 CUDA parameters (no CPU fallback)")
-            sizes = [(p.numel() + 3) // 4 * 4 for p in ps]          # keep every view 16-byte aligned
+            sizes = [(p.numel() + 7) // 8 * 8 for p in ps]          # every fp32 AND bf16-shadow view 16-byte aligned
             plan.append((ps, sizes))
         if not any(ps for ps, _ in plan):
             raise _lib.EegxError("FlatAdamW.step() called before any backward pass")
@@ -54,6 +54,7 @@ class FlatAdamW(torch.optim.Optimizer):
                 continue
             total = sum(sizes)
             flat_p = torch.zeros(total, device=dev)
+            flat_w16 = torch.zeros(total, device=dev, dtype=torch.bfloat16)     # bf16 shadow, kept current by the AdamW kernel
             flat_g = self._all_grads[base:base + total]
             base += total
             off = 0
@@ -63,9 +64,11 @@ class FlatAdamW(torch.optim.Optimizer):
                 flat_g[off:off + k].copy_(p.grad.reshape(-1))
                 p.data = flat_p[off:off + k].view_as(p)
                 p.grad = flat_g[off:off + k].view_as(p)
+                p._eegx_w16 = flat_w16[off:off + k].view_as(p)
                 off += n
+            flat_w16.copy_(flat_p)
             flats.append(dict(p=flat_p, g=flat_g, m=torch.zeros_like(flat_p), v=torch.zeros_like(flat_p),
-                              params=ps))
+                              w16=flat_w16, params=ps))
         self._flat = flats
         self._norm_sq = torch.zeros(1, device=dev)
         self._ws = torch.empty(_lib.lib().eegx_sumsq_workspace_bytes(), dtype=torch.uint8, device=dev)
@@ -110,9 +113,11 @@ class FlatAdamW(torch.optim.Optimizer):
             _lib.check(lib.eegx_adamw_clip_f32(
                 _lib.ptr(f['p']), _lib.ptr(f['g']), _lib.ptr(f['m']), _lib.ptr(f['v']), f['p'].numel(),
                 float(group['lr']), float(b1), float(b2), float(group['eps']), float(group['weight_decay']),
-                self._step, norm_ptr, float(max_grad_norm or 0.0), float(self.grad_scale), st),
+                self._step, norm_ptr, float(max_grad_norm or 0.0), float(self.grad_scale), _lib.ptr(f['w16']), st),
                 "eegx_adamw_clip_f32")
-        nn_ops.clear_pack_cache()      # parameters changed behind autograd's back: repack bf16 copies
+            for p in f['params']:
+                p._eegx_w16_ver = p._version       # the shadow matches the parameter as of now
+        nn_ops.clear_pack_cache()      # parameters changed behind autograd's back: derived packs are stale
         return None
 
     def grad_norm(self) -> torch.Tensor:

@@ -153,6 +153,8 @@ class EEGTrainer:
             self.optimizer.zero_grad()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        from . import nn_ops
+        nn_ops.clear_pack_cache()      # derived weight packs must be (re)built INSIDE the graph, from live weights
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self._static_loss = self._eager_step(self._static)

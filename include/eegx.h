@@ -154,13 +154,15 @@ int eegx_gemm_bf16(const eegx_gemm_desc* desc, const void* A, const void* B, con
  *                         p *= 1 - lr*wd;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2
  *                         p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
  *                       grad_scale folds a constant factor on g (e.g. 1/world_size).
+ *                       w16 (nullable): n bf16 values, receives the updated parameters rounded to bf16 -- the
+ *                       operand copy the GEMMs of the next step read (no separate cast kernels).
  * ------------------------------------------------------------------------ */
 size_t eegx_sumsq_workspace_bytes(void);
 int eegx_sumsq_f32(const float* g, int64_t n, float* out, int accumulate, void* workspace,
                    size_t workspace_bytes, void* stream);
 int eegx_adamw_clip_f32(float* p, const float* g, float* m, float* v, int64_t n, float lr,
                         float beta1, float beta2, float eps, float weight_decay, int64_t step,
-                        const float* grad_norm_sq, float max_norm, float grad_scale, void* stream);
+                        const float* grad_norm_sq, float max_norm, float grad_scale, void* w16, void* stream);
 
 
 /* ------------------------------------------------------------------------

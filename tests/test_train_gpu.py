@@ -136,33 +136,40 @@ def test_high_density_long_window_step():
 
 
 def test_cuda_graph_replay_matches_eager():
+    """Same weights, same batches, dropout off: a model stepped eagerly and a model stepped through the
+    captured graph follow the same loss trajectory while the weights move (so the graph must be reading the
+    live weights, not copies frozen at capture time)."""
     counts = {'frontal': 16, 'temporal': 16, 'central': 16, 'parietal': 16}
-    torch.manual_seed(0)
-    model = EEGDecodingModel(n_timepoints=33, region_channel_counts=counts).cuda().train()
-    _zero_dropout(model)
-    cfg = dict(tr.CONFIG, accumulation_steps=1, warmup_steps=500)       # lr stays ~0: weights do not move
-    opt = tr.build_optimizer(model, cfg)
-    sched = tr.cosine_schedule_with_warmup(opt, 10 ** 9, 10 ** 9 + 1)
-    t = tr.EEGTrainer(model, None, None, None, opt, sched, cfg)
-    batches = [{k: (v if not isinstance(v, list) else [r.cuda() for r in v]) for k, v in b.items()}
-               for b in _batches(3, 4, counts, 33, seed=9)]
-    flat = [{'eeg0': b['eeg'][0], 'eeg1': b['eeg'][1], 'eeg2': b['eeg'][2], 'eeg3': b['eeg'][3],
-             'decoder_input_ids': b['decoder_input_ids'].cuda(), 'labels': b['labels'].cuda()} for b in batches]
 
     class _T(tr.EEGTrainer):
         def _regions(self, batch):
             return [batch['eeg0'], batch['eeg1'], batch['eeg2'], batch['eeg3']]
 
-    t.__class__ = _T
+    def make():
+        torch.manual_seed(0)
+        model = EEGDecodingModel(n_timepoints=33, region_channel_counts=counts).cuda().train()
+        _zero_dropout(model)
+        cfg = dict(tr.CONFIG, accumulation_steps=1)
+        opt = tr.build_optimizer(model, cfg)
+        sched = tr.cosine_schedule_with_warmup(opt, 1, 100)
+        return _T(model, None, None, None, opt, sched, cfg), opt
+
+    flat = [{'eeg0': b['eeg'][0].cuda(), 'eeg1': b['eeg'][1].cuda(), 'eeg2': b['eeg'][2].cuda(), 'eeg3': b['eeg'][3].cuda(),
+             'decoder_input_ids': b['decoder_input_ids'].cuda(), 'labels': b['labels'].cuda()}
+            for b in _batches(1, 4, counts, 33, seed=9)] * 6     # one batch, repeated: the loss falls quickly
+    t_e, opt_e = make()
     eager = []
     for b in flat:
-        eager.append(t.train_step(b).item())
-        gnorm_eager = None
-        t._optimizer_step(step_scheduler=False)
-        gnorm_eager = float(opt.grad_norm())
-    t.capture(flat[0])
-    for b, ref in zip(flat, eager):
-        loss = t.train_step(b)
-        t._optimizer_step(step_scheduler=False)
-        assert abs(loss.item() - ref) <= 2e-3 * abs(ref)
-    assert abs(float(opt.grad_norm()) - gnorm_eager) <= 2e-2 * gnorm_eager
+        eager.append(t_e.train_step(b).item())
+        t_e._optimizer_step(step_scheduler=True)
+    t_g, opt_g = make()
+    got = []
+    for i, b in enumerate(flat):
+        if i == 2:
+            t_g.capture(flat[0])
+        got.append(t_g.train_step(b).item())
+        t_g._optimizer_step(step_scheduler=True)
+    assert eager[0] - eager[-1] > 0.3                     # the weights really moved
+    for a, e in zip(got, eager):
+        assert abs(a - e) <= 5e-3 * abs(e), (got, eager)
+    assert abs(float(opt_g.grad_norm()) - float(opt_e.grad_norm())) <= 3e-2 * float(opt_e.grad_norm())
