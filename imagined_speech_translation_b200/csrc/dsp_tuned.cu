@@ -136,6 +136,14 @@ __device__ __forceinline__ float fast_log2(float x) {   // x >= 4*log_eps > 0: n
     return y;
 }
 
+
+// ---- packed f32x2 arithmetic for the half-row FIR (PK variant) ----
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk2(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__host__ __device__ constexpr int padded32(int o) { return o + 4 * (o >> 5); }   // 4 pad floats per 32: conflict-free 128-bit access
+
 // ---- TMA (1-D bulk copy) + mbarrier helpers ----
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -169,9 +177,14 @@ __device__ __forceinline__ void issue_tile_loads(const TunedArgs& a, float* xs, 
                     (unsigned)(T * sizeof(float)), bar);
 }
 
-template <int ROWS, int NT>
+// PK (ROWS == 1 only): the FIR runs on packed f32x2 values -- the row's two halves (t, t + 1024) move through
+// it as (lo, hi) pairs (FFMA2 with the taps as scalar-broadcast operands): half the FIR's issue slots.  The
+// pairs are interleaved into the STFT scratch region (free during the FIR) with the padded32 layout.
+template <int ROWS, int NT, bool PK>
 __global__ void __launch_bounds__(NT, Cfg<ROWS, NT>::CTAS_PER_SM)
 dsp_tuned_kernel(const __grid_constant__ TunedArgs a) {
+    static_assert(!PK || (ROWS == 1 && Cfg<ROWS, NT>::NGROUPS * 256 >= padded32(2 * (T / 2 + 64)) && NT >= 64),
+                  "packed FIR: one row per tile, pairs must fit the STFT scratch");
     using C = Cfg<ROWS, NT>;
     constexpr int NWARPS = C::NWARPS;
     extern __shared__ __align__(128) float smem[];
@@ -226,6 +239,66 @@ dsp_tuned_kernel(const __grid_constant__ TunedArgs a) {
         mbar_wait(bar, phase);
         phase ^= 1;
 
+        if constexpr (PK) {
+            // ---------------- interleave: pair p = (x[p - 32], x[p - 32 + T/2]), p in [0, T/2 + 64) ----------------
+            float* xi = scr;
+            for (int u = tid; u < (T / 2 + 64) / 4; u += NT) {
+                const float4 va = *reinterpret_cast<const float4*>(xs + 4 * u);
+                const float4 vb = *reinterpret_cast<const float4*>(xs + T / 2 + 4 * u);
+                float* d = xi + padded32(8 * u);
+                *reinterpret_cast<float4*>(d) = make_float4(va.x, vb.x, va.y, vb.y);
+                *reinterpret_cast<float4*>(d + 4) = make_float4(va.z, vb.z, va.w, vb.w);
+            }
+            __syncthreads();
+            // xs is free already: fetch the next tile while the FIR and the STFT run
+            if (tid == 0 && tile + gridDim.x < ntiles) issue_tile_loads<ROWS>(a, xs, bar, (tile + gridDim.x) * ROWS);
+            // ---------------- FIR: thread j < 64 owns pair-outputs t = 16 j .. 16 j + 15 ----------------
+            if (tid < T / 32) {
+                f2 acc[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) acc[e] = 0ull;
+                const float* src = xi + 36 * tid;                       // padded32(32 * tid)
+#pragma unroll
+                for (int sl = 0; sl < 40; ++sl) {
+                    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(src + 4 * sl + 4 * (sl >> 3));
+                    const f2 in[2] = {v.x, v.y};
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int i = 2 * sl + u;                       // input pair i feeds output e with tap d = i - e
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            const int d = i - e;
+                            if (d >= 0 && d <= 64) acc[e] = fma2(in[u], pk2(a.taps_rev[d], a.taps_rev[d]), acc[e]);
+                        }
+                    }
+                }
+                float ya[16], yb[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) upk2(acc[e], ya[e], yb[e]);
+                float* yrow = ys;
+                float4* da = reinterpret_cast<float4*>(yrow + 128 + 16 * tid);
+                float4* db = reinterpret_cast<float4*>(yrow + 128 + T / 2 + 16 * tid);
+#pragma unroll
+                for (int v4 = 0; v4 < 4; ++v4) {
+                    da[v4] = make_float4(ya[4 * v4], ya[4 * v4 + 1], ya[4 * v4 + 2], ya[4 * v4 + 3]);
+                    db[v4] = make_float4(yb[4 * v4], yb[4 * v4 + 1], yb[4 * v4 + 2], yb[4 * v4 + 3]);
+                }
+                if (tid <= 8) {           // reflect copy on the left: index -t for t in [1, 128]
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const int t = 16 * tid + e;
+                        if (t >= 1 && t <= 128) yrow[128 - t] = ya[e];
+                    }
+                }
+                if (tid >= 55) {          // reflect copy on the right: index 2(T-1)-t for t in [T-129, T-2]
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const int t = T / 2 + 16 * tid + e;
+                        if (t >= T - 129 && t <= T - 2) yrow[2 * (T - 1) - t + 128] = yb[e];
+                    }
+                }
+            }
+        } else {
         // ------------------------------ FIR ------------------------------
         // lanes alternate rows; a thread owns outputs t = 8j .. 8j+7 of its row
         for (int th = tid; th < ROWS * 256; th += NT) {
@@ -267,9 +340,10 @@ dsp_tuned_kernel(const __grid_constant__ TunedArgs a) {
                 }
             }
         }
+        }
         __syncthreads();
         // xs is free again: fetch the next tile while the STFT runs
-        if (tid == 0 && tile + gridDim.x < ntiles) issue_tile_loads<ROWS>(a, xs, bar, (tile + gridDim.x) * ROWS);
+        if (!PK && tid == 0 && tile + gridDim.x < ntiles) issue_tile_loads<ROWS>(a, xs, bar, (tile + gridDim.x) * ROWS);
 
         // ------------------------------ STFT ------------------------------
         // rows sit in Ls with the same 16-byte phase as their global address
@@ -449,15 +523,15 @@ bool dsp_tuned_supported(const eegx_dsp_plan* p) {
 int dsp_tuned_table_floats() { return 8 * LANE_TABLE; }
 void dsp_tuned_fill_tables(float* host) { fill_lane_tables(host); }
 
-template <int ROWS, int NT>
+template <int ROWS, int NT, bool PK = false>
 int launch_variant(const TunedArgs& a, cudaStream_t st) {
     using C = Cfg<ROWS, NT>;
-    EEGX_CUDA_CHECK(cudaFuncSetAttribute(dsp_tuned_kernel<ROWS, NT>,
+    EEGX_CUDA_CHECK(cudaFuncSetAttribute(dsp_tuned_kernel<ROWS, NT, PK>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
     const long long ntiles = (a.rows + ROWS - 1) / ROWS;
     const long long max_ctas = (long long)C::CTAS_PER_SM * kNumSMsB200;
     const int grid = (int)(ntiles < max_ctas ? ntiles : max_ctas);
-    dsp_tuned_kernel<ROWS, NT><<<grid, NT, C::SMEM_BYTES, st>>>(a);
+    dsp_tuned_kernel<ROWS, NT, PK><<<grid, NT, C::SMEM_BYTES, st>>>(a);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
 }
@@ -475,6 +549,7 @@ int launch_dsp_tuned(const eegx_dsp_plan* plan, const DspArgs& d, cudaStream_t s
     for (int i = 0; i < 65; ++i) a.taps_rev[i] = plan->h_taps[64 - i];
     switch (plan->tuned_variant) {
         case 3: return launch_dsp_pair(plan, d, st);    // packed f32x2, 2 rows per tile (dsp_tuned2.cu)
+        case 4: return launch_variant<1, 96, true>(a, st);   // 1 row per tile, packed half-row FIR
         case 1: return launch_variant<1, 96>(a, st);    // 4 CTAs/SM x 3 warps, 1 row per tile
         case 2: return launch_variant<2, 192>(a, st);   // 2 CTAs/SM x 6 warps, 2 rows per tile
         default: return launch_variant<1, 96>(a, st);
