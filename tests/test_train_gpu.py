@@ -173,3 +173,38 @@ def test_cuda_graph_replay_matches_eager():
     for a, e in zip(got, eager):
         assert abs(a - e) <= 5e-3 * abs(e), (got, eager)
     assert abs(float(opt_g.grad_norm()) - float(opt_e.grad_norm())) <= 3e-2 * float(opt_e.grad_norm())
+
+
+def test_step_is_bit_reproducible():
+    """Two identical runs (same seed, same batches, dropout ON) give bit-identical losses and gradients:
+    every reduction in libeegx has a fixed summation order and the dropout masks are counter based."""
+    from imagined_speech_translation_b200 import fused
+    counts = {'frontal': 16, 'temporal': 16, 'central': 16, 'parietal': 16}
+    batches = _batches(3, 4, counts, 33, seed=21)
+
+    def run():
+        torch.manual_seed(0)
+        fused.set_seed(1234)
+        model = EEGDecodingModel(n_timepoints=33, region_channel_counts=counts).cuda().train()
+        cfg = dict(tr.CONFIG, accumulation_steps=1, warmup_steps=1)
+        opt = tr.build_optimizer(model, cfg)
+        sched = tr.cosine_schedule_with_warmup(opt, 1, 100)
+        t = tr.EEGTrainer(model, None, None, None, opt, sched, cfg)
+        losses = []
+        for b in batches:
+            losses.append(t.train_step(b).item())
+            t._optimizer_step(step_scheduler=True)
+        t.train_step(batches[0])
+        names = ["brain_encoder.region_encoders.frontal.conv1.weight", "brain_encoder.region_encoders.parietal.bn3.weight",
+                 "brain_encoder.region_encoders.central.attn_layers.1.attn.in_proj_weight",
+                 "brain_encoder.region_encoders.temporal.attn_layers.0.ffn.gate.bias",
+                 "brain_encoder.feature_enhancer.0.weight", "bart_decoder.bart.model.decoder.layers.3.fc1.weight",
+                 "bart_decoder.bart.model.shared.weight", "bart_decoder.eeg_to_bart.1.weight"]
+        params = dict(model.named_parameters())
+        return losses, {n: params[n].grad.detach().clone() for n in names}
+
+    l1, g1 = run()
+    l2, g2 = run()
+    assert l1 == l2
+    for n in g1:
+        assert torch.equal(g1[n], g2[n]), n
