@@ -431,8 +431,8 @@ def run_ours(args, rank, world, local_rank):
         pairs.append((a_, b_))
     torch.cuda.synchronize()
     ev_overhead_ms = float(np.median([a_.elapsed_time(b_) for a_, b_ in pairs]))
-    gemm_ms = sum(max(a.elapsed_time(b) - ev_overhead_ms, 0.0) for a, b, _ in rec)
-    gemm_flops = sum(f for _, _, f in rec)
+    gemm_ms = sum(max(r[0].elapsed_time(r[1]) - ev_overhead_ms, 0.0) for r in rec)
+    gemm_flops = sum(r[2] for r in rec)
 
     dsp = bench_dsp(fe, dev, rank, world, args, barrier)
 

@@ -218,35 +218,40 @@ __device__ __forceinline__ void patch_write(unsigned char* patch, int lane, int 
     }
 }
 
-// the patch (32 rows x 128 bytes) -> global: 8 lanes write one row's 128 bytes, 4 rows per instruction
+// the patch (32 rows x 128 bytes) -> global: 8 lanes write one row's 128 bytes, 4 rows per instruction.
+// With `accumulate` the eight old values are fetched first, all in flight together (a load -> add -> store
+// chain per row exposed eight global-memory latencies per chunk and made the small weight-gradient GEMMs,
+// which accumulate straight into the gradient buffers, ~3x slower than their forward twins).
 __device__ __forceinline__ void patch_flush(const GemmParams& p, const unsigned char* patch, int lane, long long row0,
                                             long long col0, long long bi) {
     const int piece = lane & 7;
     const int epp = p.out_f32 ? 4 : 8;                   // elements per 16-byte piece
     const long long col = col0 + piece * epp;
+    const bool col_ok = col < p.N;
+    const size_t es = p.out_f32 ? 4 : 2;
+    unsigned char* base = static_cast<unsigned char*>(p.D) + (size_t)(bi * p.stride_d + col) * es;
+    uint4 old[8];
+    if (p.accumulate) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const long long row = row0 + 4 * it + (lane >> 3);
+            old[it] = make_uint4(0u, 0u, 0u, 0u);
+            if (row < p.M && col_ok) old[it] = *reinterpret_cast<const uint4*>(base + (size_t)row * p.ldd * es);
+        }
+    }
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
         const int r = 4 * it + (lane >> 3);
         const long long row = row0 + r;
-        if (row < p.M && col < p.N) {
+        if (row < p.M && col_ok) {
             uint4 val = *reinterpret_cast<const uint4*>(patch + r * EPI_ROW_BYTES + piece * 16);
-            const long long off = bi * p.stride_d + row * p.ldd + col;
-            if (p.out_f32) {
-                float4* g = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.D) + off);
-                if (p.accumulate) {
-                    const float4 old = *g;
-                    val.x = __float_as_uint(__uint_as_float(val.x) + old.x);
-                    val.y = __float_as_uint(__uint_as_float(val.y) + old.y);
-                    val.z = __float_as_uint(__uint_as_float(val.z) + old.z);
-                    val.w = __float_as_uint(__uint_as_float(val.w) + old.w);
-                }
-                *reinterpret_cast<uint4*>(g) = val;
-            } else {
-                uint4* g = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.D) + off);
-                if (p.accumulate) {
-                    const uint4 old = *g;
-                    const unsigned* o = &old.x;
-                    unsigned* w = &val.x;
+            if (p.accumulate) {
+                unsigned* w = &val.x;
+                const unsigned* o = &old[it].x;
+                if (p.out_f32) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) w[k] = __float_as_uint(__uint_as_float(w[k]) + __uint_as_float(o[k]));
+                } else {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
@@ -254,8 +259,8 @@ __device__ __forceinline__ void patch_flush(const GemmParams& p, const unsigned 
                         w[k] = pack_bf16(a.x + b.x, a.y + b.y);
                     }
                 }
-                *g = val;
             }
+            *reinterpret_cast<uint4*>(base + (size_t)row * p.ldd * es) = val;
         }
     }
 }

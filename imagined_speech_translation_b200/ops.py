@@ -79,5 +79,5 @@ def gemm(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, 
                                          _lib.ptr(out), _lib.stream_ptr()), "eegx_gemm_bf16")
     if GEMM_TIMING is not None:
         e1.record()
-        GEMM_TIMING.append((e0, e1, 2.0 * M * N * K * batch))
+        GEMM_TIMING.append((e0, e1, 2.0 * M * N * K * batch, (batch, M, N, K, int(a_mn_major), int(b_mn_major))))
     return out
