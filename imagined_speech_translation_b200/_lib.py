@@ -85,6 +85,7 @@ SIGNATURES.update({
     "eegx_colreduce_workspace_bytes": (_SZ, [_I64]),
     "eegx_colsum_bf16": (_I, [_P, _I64, _I64, _I64, _P, _I, _P, _SZ, _P]),
     "eegx_accumulate_partials_f32": (_I, [_P, _I64, _I64, _P, _I, _P]),
+    "eegx_accumulate_conv_wgrad_f32": (_I, [_P, _I64, _I64, _I64, _I64, _P, _I, _P]),
     "eegx_bn_stats_bf16": (_I, [_P, _I64, _I64, _I64, _I64, _F, _P, _P, _P, _P, _F, _P, _SZ, _P]),
     "eegx_bn_act_fwd_bf16": (_I, [_P] * 10 + [_I, _P, _I64, _I64, _I64, _I64] + _RNG + [_P]),
     "eegx_bn_act_bwd_bf16": (_I, [_P] * 11 + [_I, _I, _P, _P, _P, _P, _SZ, _I64, _I64, _I64, _I64] + _RNG + [_P]),

@@ -526,6 +526,25 @@ zero_invalid_rows_kernel(__nv_bfloat16* __restrict__ out, RowGeom g, int pad, in
     }
 }
 
+// Conv1d weight gradient: the GEMM produces (s partials of) dW[co][tap * Cin + ci]; the parameter is laid out
+// (Cout, Cin, k).  dst[co][ci][tap] (+)= sum_s part[s][co][tap * Cin + ci] -- partial folding, permutation and
+// gradient accumulation in one pass.
+__global__ void __launch_bounds__(256)
+accumulate_conv_wgrad_kernel(const float* __restrict__ part, int s, long long n, int Cin, int k, float* __restrict__ dst,
+                             int accumulate) {
+    const long long per_co = (long long)Cin * k;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        // i indexes the destination (co, ci, tap): coalesced writes, strided (L2-resident) reads
+        const long long co = i / per_co;
+        const int rem = (int)(i - co * per_co);
+        const int ci = rem / k, tap = rem - ci * k;
+        const long long src = co * per_co + (long long)tap * Cin + ci;
+        float a = accumulate ? dst[i] : 0.0f;
+        for (int j = 0; j < s; ++j) a += __ldg(part + (long long)j * n + src);
+        dst[i] = a;
+    }
+}
+
 int ew_grid(long long n) {
     long long b = (n + 255) / 256;
     const long long cap = (long long)kNumSMsB200 * 8;
@@ -581,6 +600,20 @@ int eegx_accumulate_partials_f32(const float* part, int64_t s, int64_t n, float*
     EEGX_REQUIRE(eegx::aligned16(part) && eegx::aligned16(dst), EEGX_ERR_ALIGN, "accumulate_partials: 16-byte alignment");
     accumulate_partials_kernel<<<ew_grid(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(part, (int)s, n / 4, dst,
                                                                                               accumulate);
+    EEGX_CUDA_CHECK(cudaGetLastError());
+    return EEGX_OK;
+}
+
+int eegx_accumulate_conv_wgrad_f32(const float* part, int64_t s, int64_t Cout, int64_t Cin, int64_t k, float* dst,
+                                   int accumulate, void* stream) {
+    if (int rc = eegx::require_sm100()) return rc;
+    EEGX_REQUIRE(s >= 1 && Cout >= 0 && Cin >= 1 && k >= 1 && Cin * k < (1LL << 31), EEGX_ERR_SHAPE,
+                 "accumulate_conv_wgrad: bad sizes");
+    const long long n = Cout * Cin * k;
+    if (n == 0) return EEGX_OK;
+    EEGX_REQUIRE(part && dst, EEGX_ERR_ARG, "accumulate_conv_wgrad: NULL pointer");
+    accumulate_conv_wgrad_kernel<<<ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(part, (int)s, n, (int)Cin, (int)k,
+                                                                                          dst, accumulate);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
 }

@@ -127,6 +127,13 @@ def accumulate_partials(part: torch.Tensor, into: torch.Tensor) -> None:
                                                        _lib.stream_ptr()), "eegx_accumulate_partials_f32")
 
 
+def accumulate_conv_wgrad(part: torch.Tensor, dst: torch.Tensor, Cin: int, k: int, accumulate: bool) -> None:
+    """dst (Cout, Cin, k) (+)= sum_s part[s] with part (s, Cout, k*Cin) in the conv GEMM's K order."""
+    s, Cout = part.shape[0], part.shape[1]
+    _lib.check(_lib.lib().eegx_accumulate_conv_wgrad_f32(_lib.ptr(part), s, Cout, Cin, k, _lib.ptr(dst), int(accumulate),
+                                                         _lib.stream_ptr()), "eegx_accumulate_conv_wgrad_f32")
+
+
 # ------------------------------------------------------------------------------------------ LayerNorm
 class _LayerNorm(torch.autograd.Function):
     @staticmethod
@@ -367,6 +374,11 @@ class _BnAct(torch.autograd.Function):
             _lib.ptr(gr), _lib.ptr(br), res_mode, int(training), _lib.ptr(da[PAD:]),
             _lib.ptr(dr[PAD:]) if res_mode else None, _lib.ptr(sums), _lib.ptr(ws), ws.numel(), B, T, PAD, C_,
             _lib.ptr(rng), site, p, _lib.stream_ptr()), "eegx_bn_act_bwd_bf16")
+        targets = [(gamma_a, sums[1]), (beta_a, sums[0])] + ([(gamma_r, sums[2]), (beta_r, sums[0])] if res_mode == 2 else [])
+        bufs = [grad_buffer(p_) for p_, _ in targets]
+        if all(b is not None for b in bufs):       # one multi-tensor add straight into the gradient buffers
+            torch._foreach_add_(bufs, [v for _, v in targets])
+            return da, None, None, dr, None, None, None, None, None, None, None, None, None, None, None
         dga, dba = sums[1].to(gamma_a.dtype), sums[0].to(beta_a.dtype)
         dgr = sums[2].to(gamma_r.dtype) if res_mode == 2 else None
         dbr = sums[0].to(beta_r.dtype) if res_mode == 2 else None

@@ -69,7 +69,7 @@ def _w_conv_dgrad(w):        # (Cout, Cin, k) -> (k*Cout, Cin) bf16 with taps fl
     return _cached(w, "convd", lambda _: _bf16_src(w).flip(2).permute(2, 0, 1).reshape(-1, w.shape[1]).contiguous())
 
 
-def _wgrad(dy: torch.Tensor, x: torch.Tensor, into: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+def _wgrad(dy: torch.Tensor, x: torch.Tensor, into: Optional[torch.Tensor] = None, raw: bool = False):
     """dW (N, K) fp32 = dy^T x, reduction over the R rows.  The output is small (N x K) while R is
     ~10^4, so a plain launch fills only N*K / (128*256) of the 148 SMs: split the reduction into s
     row-chunks run as GEMM batches (s * tiles ~ one wave) and add the partials in a fixed order.
@@ -82,6 +82,13 @@ def _wgrad(dy: torch.Tensor, x: torch.Tensor, into: Optional[torch.Tensor] = Non
     s = 1
     while tiles * s * 2 <= 160 and R % (s * 2) == 0 and (R // (s * 2)) % 8 == 0 and R // (s * 2) >= 512:
         s *= 2
+    if raw:                                           # (s, N, K) partials, the caller folds them
+        if s == 1:
+            return ops.gemm(dy, x, a_mn_major=True, b_mn_major=True, out_dtype=torch.float32).unsqueeze(0)
+        chunk = R // s
+        dy3 = dy.as_strided((s, chunk, N), (chunk * dy.stride(0), dy.stride(0), 1), dy.storage_offset())
+        x3 = x.as_strided((s, chunk, K), (chunk * x.stride(0), x.stride(0), 1), x.storage_offset())
+        return ops.gemm(dy3, x3, a_mn_major=True, b_mn_major=True, out_dtype=torch.float32)
     if s == 1:
         if into is not None:
             ops.gemm(dy, x, a_mn_major=True, b_mn_major=True, out=into, accumulate=True)
@@ -353,8 +360,10 @@ class _ConvG(torch.autograd.Function):
         dxg = dw = db = None
         if ctx.needs_input_grad[1]:
             a_view = xg.as_strided((M, k * Cin), (Cin, 1), xg.storage_offset() + (PAD - p) * Cin)
-            dwf = _wgrad(dy, a_view)                                                     # (Cout, k*Cin)
-            dw = dwf.view(Cout, k, Cin).permute(0, 2, 1)
+            part = _wgrad(dy, a_view, raw=True)                                          # (s, Cout, k*Cin)
+            gbuf = fused.grad_buffer(weight)
+            dw = None if gbuf is not None else torch.empty_like(weight, dtype=torch.float32)
+            fused.accumulate_conv_wgrad(part, gbuf if gbuf is not None else dw, Cin, k, accumulate=gbuf is not None)
         if ctx.needs_input_grad[0]:
             a = dyg.as_strided((M, k * Cout), (Cout, 1), dyg.storage_offset() + (PAD - p) * Cout)
             dxg = torch.empty(M + 2 * PAD, Cin, dtype=torch.bfloat16, device=dyg.device)

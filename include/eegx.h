@@ -220,6 +220,10 @@ int eegx_colsum_bf16(const void* y, int64_t ld, int64_t rows, int64_t C, float* 
                      size_t workspace_bytes, void* stream);
 /* dst[i] (+)= sum_s part[s * n + i]: folds the split-K partials of a weight-gradient GEMM into the gradient. */
 int eegx_accumulate_partials_f32(const float* part, int64_t s, int64_t n, float* dst, int accumulate, void* stream);
+/* nn.Conv1d weight gradient: part is s partials of the GEMM layout (Cout, k * Cin) [index tap * Cin + ci];
+ * dst, laid out like the parameter (Cout, Cin, k), (+)= their sum. */
+int eegx_accumulate_conv_wgrad_f32(const float* part, int64_t s, int64_t Cout, int64_t Cin, int64_t k, float* dst,
+                                   int accumulate, void* stream);
 int eegx_bn_stats_bf16(const void* y, int64_t B, int64_t T, int64_t pad, int64_t C, float eps, float* mean,
                        float* rstd, float* running_mean, float* running_var, float momentum, void* workspace,
                        size_t workspace_bytes, void* stream);
