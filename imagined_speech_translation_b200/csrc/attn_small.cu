@@ -88,6 +88,7 @@ __device__ __forceinline__ unsigned long long pgroup(int bh, int i, int j) {
 template <int HD, int NT>
 __global__ void __launch_bounds__(NT * 32)
 attn_fwd_kernel(const AttnArgs a) {
+    EEGX_PDL_SYNC();
     constexpr int LD = HD + 8, ROWS = NT * 16;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     bf16* Qs = reinterpret_cast<bf16*>(smem_raw);
@@ -204,6 +205,7 @@ __device__ __forceinline__ void store_rows(bf16* base, long long rs, int row_lo,
 template <int HD, int NT>
 __global__ void __launch_bounds__(2 * NT * 32, 2)
 attn_bwd_kernel(const AttnArgs a) {
+    EEGX_PDL_SYNC();
     constexpr int LD = HD + 8, ROWS = NT * 16;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     bf16* Qs = reinterpret_cast<bf16*>(smem_raw);
@@ -367,10 +369,10 @@ int launch(const AttnArgs& a, bool backward, cudaStream_t st) {
                                  : (size_t)3 * ROWS * LD * sizeof(bf16);
     if (backward) {
         EEGX_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attn_bwd_kernel<HD, NT><<<a.B * a.H, 2 * NT * 32, smem, st>>>(a);
+        eegx::launch(attn_bwd_kernel<HD, NT>, a.B * a.H, 2 * NT * 32, smem, st, a);
     } else {
         EEGX_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attn_fwd_kernel<HD, NT><<<a.B * a.H, NT * 32, smem, st>>>(a);
+        eegx::launch(attn_fwd_kernel<HD, NT>, a.B * a.H, NT * 32, smem, st, a);
     }
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;

@@ -74,6 +74,7 @@ __device__ double percentile_linear(const float* row, long long n, double q, uns
 __global__ void __launch_bounds__(256)
 robust_fit_kernel(const float* __restrict__ x, long long n, float q_lo, float q_hi, float* __restrict__ center,
                   float* __restrict__ scale) {
+    EEGX_PDL_SYNC();
     __shared__ unsigned hist[256];
     __shared__ unsigned bcast[2];
     const float* row = x + (long long)blockIdx.x * n;
@@ -90,6 +91,7 @@ robust_fit_kernel(const float* __restrict__ x, long long n, float q_lo, float q_
 // population std of each row of an (B, n) matrix; one CTA per row, fp64 fixed-order reduction
 __global__ void __launch_bounds__(256)
 row_std_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+    EEGX_PDL_SYNC();
     __shared__ double rs[8], rq[8];
     const float* row = x + (long long)blockIdx.x * n;
     double s = 0.0, q = 0.0;
@@ -120,6 +122,7 @@ __global__ void __launch_bounds__(256)
 augment_kernel(const float* __restrict__ x, float* __restrict__ out, long long B, int C, int T,
                const float* __restrict__ sigma, const float* __restrict__ scale, const int* __restrict__ shift,
                DropoutCfg dc) {
+    EEGX_PDL_SYNC();
     const long long per = (long long)C * T;
     const long long total = B * per;
     uint2 key = make_uint2(0u, 0u);
@@ -158,7 +161,7 @@ int eegx_robust_fit_f32(const float* x, int64_t C, int64_t n, float q_lo, float 
     EEGX_REQUIRE(q_lo >= 0.0f && q_hi <= 100.0f && q_lo < q_hi, EEGX_ERR_ARG, "robust_fit: need 0 <= q_lo < q_hi <= 100");
     if (C == 0) return EEGX_OK;
     EEGX_REQUIRE(x && center && scale, EEGX_ERR_ARG, "robust_fit: NULL pointer");
-    robust_fit_kernel<<<(unsigned)C, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, q_lo, q_hi, center, scale);
+    eegx::launch(robust_fit_kernel, (unsigned)C, 256, 0, static_cast<cudaStream_t>(stream), x, n, q_lo, q_hi, center, scale);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
 }
@@ -168,7 +171,7 @@ int eegx_region_std_f32(const float* x, int64_t B, int64_t n, float* out, void* 
     EEGX_REQUIRE(B >= 0 && n >= 1 && B < (1LL << 31), EEGX_ERR_SHAPE, "region_std: need n >= 1");
     if (B == 0) return EEGX_OK;
     EEGX_REQUIRE(x && out, EEGX_ERR_ARG, "region_std: NULL pointer");
-    row_std_kernel<<<(unsigned)B, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, out);
+    eegx::launch(row_std_kernel, (unsigned)B, 256, 0, static_cast<cudaStream_t>(stream), x, n, out);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
 }
@@ -184,7 +187,7 @@ int eegx_augment_f32(const float* x, float* out, int64_t B, int64_t C, int64_t T
     long long blocks = (B * C * T + 255) / 256;
     const long long cap = (long long)kNumSMsB200 * 8;
     if (blocks > cap) blocks = cap;
-    augment_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, B, (int)C, (int)T, sigma, scale,
+    eegx::launch(augment_kernel, (int)blocks, 256, 0, static_cast<cudaStream_t>(stream), x, out, B, (int)C, (int)T, sigma, scale,
                                                                               reinterpret_cast<const int*>(shift), dc);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;

@@ -1,4 +1,6 @@
 // Version, error reporting and the architecture gate of libeegx.so.
+#include <stdlib.h>
+
 #include "eegx_common.h"
 
 namespace eegx {
@@ -14,6 +16,11 @@ int set_error(int code, const char* fmt, ...) {
     vsnprintf(error_buffer(), 512, fmt, ap);
     va_end(ap);
     return code;
+}
+
+bool pdl_enabled() {
+    static const bool on = [] { const char* v = getenv("EEGX_PDL"); return v != nullptr && atoi(v) != 0; }();
+    return on;
 }
 
 int require_sm100() {

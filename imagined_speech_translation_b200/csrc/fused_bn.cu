@@ -82,6 +82,7 @@ __device__ __forceinline__ float2 ld2(const __nv_bfloat16* p) {
 // ------------------------------------------------------------------ BatchNorm statistics
 __global__ void __launch_bounds__(CR_THREADS)
 bn_stats_partial_kernel(const __nv_bfloat16* __restrict__ y, RowGeom g, int C, float* __restrict__ part) {
+    EEGX_PDL_SYNC();
     col_reduce<2>(g, C, part, [&](long long m, int c, float (&acc)[2][2]) {
         const float2 v = ld2(y + m * C + c);
         acc[0][0] += v.x; acc[0][1] += v.y;
@@ -92,6 +93,7 @@ bn_stats_partial_kernel(const __nv_bfloat16* __restrict__ y, RowGeom g, int C, f
 // plain column sums of a (rows, C) bf16 matrix (bias gradients): same skeleton, every row valid
 __global__ void __launch_bounds__(CR_THREADS)
 colsum_partial_kernel(const __nv_bfloat16* __restrict__ y, long long ld, RowGeom g, int C, float* __restrict__ part) {
+    EEGX_PDL_SYNC();
     col_reduce<1>(g, C, part, [&](long long m, int c, float (&acc)[1][2]) {
         const float2 v = ld2(y + m * ld + c);
         acc[0][0] += v.x; acc[0][1] += v.y;
@@ -104,6 +106,7 @@ __global__ void bn_stats_final_kernel(const float* __restrict__ part, int nslabs
                                       float* __restrict__ mean, float* __restrict__ rstd,
                                       float* __restrict__ running_mean, float* __restrict__ running_var,
                                       float momentum) {
+    EEGX_PDL_SYNC();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     double s = 0.0, q = 0.0;
@@ -136,6 +139,7 @@ struct BnSide {
 __global__ void __launch_bounds__(256)
 bn_act_fwd_kernel(BnSide a, BnSide r, int res_mode, __nv_bfloat16* __restrict__ out, RowGeom g, int pad, int C,
                   DropoutCfg dc) {
+    EEGX_PDL_SYNC();
     const DropoutGen gen(dc);
     const int c8 = C >> 3;
     const long long total = (g.M + 2 * pad) * c8;
@@ -200,6 +204,7 @@ __device__ __forceinline__ void bn_act_dpre(const BnSide& a, const BnSide& r, in
 __global__ void __launch_bounds__(CR_THREADS)
 bn_act_bwd_reduce_kernel(BnSide a, BnSide r, int res_mode, const __nv_bfloat16* __restrict__ dout, RowGeom g, int C,
                          DropoutCfg dc, float* __restrict__ part) {
+    EEGX_PDL_SYNC();
     const DropoutGen gen(dc);
     col_reduce<3>(g, C, part, [&](long long m, int c, float (&acc)[3][2]) {
         float dp[2], ha[2], hr[2];
@@ -220,6 +225,7 @@ __global__ void __launch_bounds__(256)
 bn_act_bwd_apply_kernel(BnSide a, BnSide r, int res_mode, const __nv_bfloat16* __restrict__ dout,
                         const float* __restrict__ sums, float inv_n, int train, __nv_bfloat16* __restrict__ da,
                         __nv_bfloat16* __restrict__ dr, RowGeom g, int pad, int C, DropoutCfg dc) {
+    EEGX_PDL_SYNC();
     const DropoutGen gen(dc);
     const int c2 = C >> 1;
     const long long total = (g.M + 2 * pad) * c2;
@@ -254,6 +260,7 @@ bn_act_bwd_apply_kernel(BnSide a, BnSide r, int res_mode, const __nv_bfloat16* _
 __global__ void __launch_bounds__(256)
 sum_partials_kernel(const float* __restrict__ part, int nslabs, int nacc, int C, float* __restrict__ out,
                     int accumulate = 0) {
+    EEGX_PDL_SYNC();
     __shared__ float red[8][32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + lane, k = blockIdx.y;
@@ -274,6 +281,7 @@ sum_partials_kernel(const float* __restrict__ part, int nslabs, int nacc, int C,
 // dst[i] (+)= sum_s part[s][i]  (split-K weight-gradient partials folded into the gradient buffer)
 __global__ void __launch_bounds__(256)
 accumulate_partials_kernel(const float* __restrict__ part, int s, long long n4, float* __restrict__ dst, int accumulate) {
+    EEGX_PDL_SYNC();
     const float4* p4 = reinterpret_cast<const float4*>(part);
     float4* d4 = reinterpret_cast<float4*>(dst);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -291,6 +299,7 @@ accumulate_partials_kernel(const float* __restrict__ part, int s, long long n4, 
 __global__ void __launch_bounds__(256)
 dwconv5_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                    __nv_bfloat16* __restrict__ out, RowGeom g, int pad, int C) {
+    EEGX_PDL_SYNC();
     const int c8 = C >> 3;
     const long long total = (g.M + 2 * pad) * c8;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -319,6 +328,7 @@ dwconv5_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
 __global__ void __launch_bounds__(256)
 dwconv5_bwd_data_kernel(const __nv_bfloat16* __restrict__ dout, const float* __restrict__ w,
                         __nv_bfloat16* __restrict__ dx, RowGeom g, int pad, int C) {
+    EEGX_PDL_SYNC();
     const int c8 = C >> 3;
     const long long total = (g.M + 2 * pad) * c8;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -347,6 +357,7 @@ dwconv5_bwd_data_kernel(const __nv_bfloat16* __restrict__ dout, const float* __r
 __global__ void __launch_bounds__(CR_THREADS)
 dwconv5_bwd_weight_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ x, RowGeom g,
                           int C, float* __restrict__ part) {
+    EEGX_PDL_SYNC();
     col_reduce<6>(g, C, part, [&](long long m, int c, float (&acc)[6][2]) {
         const float2 d = ld2(dout + m * C + c);
 #pragma unroll
@@ -363,6 +374,7 @@ dwconv5_bwd_weight_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfl
 // s[b][c] = (1/T) sum_t x[b, t, c]  (fp32); one CTA per (trial, 64 columns)
 __global__ void __launch_bounds__(256)
 group_mean_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ s, int Tp, int lo, int hi, int C) {
+    EEGX_PDL_SYNC();
     __shared__ float red[8][CR_COLS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int c = blockIdx.x * CR_COLS + 2 * lane;
@@ -390,6 +402,7 @@ group_mean_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ s, in
 __global__ void __launch_bounds__(256)
 se_scale_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ e, __nv_bfloat16* __restrict__ out,
                     long long B, int T, int Tp, int lo, int C, DropoutCfg dc) {
+    EEGX_PDL_SYNC();
     const DropoutGen gen(dc);
     const int c8 = C >> 3;
     const long long total = B * T * c8;
@@ -412,6 +425,7 @@ se_scale_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
 __global__ void __launch_bounds__(256)
 se_scale_bwd_x_kernel(const __nv_bfloat16* __restrict__ dout, const float* __restrict__ e,
                       __nv_bfloat16* __restrict__ dx, long long B, int T, int Tp, int lo, int C, DropoutCfg dc) {
+    EEGX_PDL_SYNC();
     const DropoutGen gen(dc);
     const int c8 = C >> 3;
     const long long total = B * T * c8;
@@ -434,6 +448,7 @@ se_scale_bwd_x_kernel(const __nv_bfloat16* __restrict__ dout, const float* __res
 __global__ void __launch_bounds__(256)
 se_scale_bwd_e_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ x,
                       float* __restrict__ de, int T, int Tp, int lo, int C, DropoutCfg dc) {
+    EEGX_PDL_SYNC();
     __shared__ float red[8][CR_COLS];
     const DropoutGen gen(dc);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -465,6 +480,7 @@ se_scale_bwd_e_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat1
 __global__ void __launch_bounds__(256)
 group_mean_bwd_kernel(const float* __restrict__ ds, __nv_bfloat16* __restrict__ dx, long long B, int T, int Tp,
                       int lo, int C, int accumulate) {
+    EEGX_PDL_SYNC();
     const int c8 = C >> 3;
     const long long total = B * T * c8;
     const float inv_t = 1.0f / (float)T;
@@ -494,6 +510,7 @@ constexpr int TR_C = 64, TR_T = 32;
 __global__ void __launch_bounds__(256)
 nct_to_rows_kernel(const float* __restrict__ x, long long x_bstride, __nv_bfloat16* __restrict__ out, int T,
                    int Tp, int lo, int C) {
+    EEGX_PDL_SYNC();
     __shared__ float tile[TR_C][TR_T + 1];
     const long long b = blockIdx.z;
     const int c0 = blockIdx.x * TR_C, t0 = blockIdx.y * TR_T;
@@ -516,6 +533,7 @@ nct_to_rows_kernel(const float* __restrict__ x, long long x_bstride, __nv_bfloat
 // zero the rows of a guarded buffer that are not valid (padding rows inside [0, M) and the guards)
 __global__ void __launch_bounds__(256)
 zero_invalid_rows_kernel(__nv_bfloat16* __restrict__ out, RowGeom g, int pad, int C) {
+    EEGX_PDL_SYNC();
     const int c8 = C >> 3;
     const long long total = (g.M + 2 * pad) * c8;
     const float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -532,6 +550,7 @@ zero_invalid_rows_kernel(__nv_bfloat16* __restrict__ out, RowGeom g, int pad, in
 __global__ void __launch_bounds__(256)
 accumulate_conv_wgrad_kernel(const float* __restrict__ part, int s, long long n, int Cin, int k, float* __restrict__ dst,
                              int accumulate) {
+    EEGX_PDL_SYNC();
     const long long per_co = (long long)Cin * k;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         // i indexes the destination (co, ci, tap): coalesced writes, strided (L2-resident) reads
@@ -585,8 +604,8 @@ int eegx_bn_stats_bf16(const void* y, int64_t B, int64_t T, int64_t pad, int64_t
     const int slabs = slabs_for(g.M, (int)C);
     float* part = static_cast<float*>(workspace);
     dim3 grid((unsigned)((C + CR_COLS - 1) / CR_COLS), (unsigned)slabs);
-    bn_stats_partial_kernel<<<grid, CR_THREADS, 0, st>>>(static_cast<const __nv_bfloat16*>(y), g, (int)C, part);
-    bn_stats_final_kernel<<<(int)((C + 127) / 128), 128, 0, st>>>(part, slabs, (int)C, (double)B * (double)T, eps, mean,
+    eegx::launch(bn_stats_partial_kernel, grid, CR_THREADS, 0, st, static_cast<const __nv_bfloat16*>(y), g, (int)C, part);
+    eegx::launch(bn_stats_final_kernel, (int)((C + 127) / 128), 128, 0, st, part, slabs, (int)C, (double)B * (double)T, eps, mean,
                                                                   rstd, running_mean, running_var, momentum);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
@@ -598,7 +617,7 @@ int eegx_accumulate_partials_f32(const float* part, int64_t s, int64_t n, float*
     if (n == 0) return EEGX_OK;
     EEGX_REQUIRE(part && dst, EEGX_ERR_ARG, "accumulate_partials: NULL pointer");
     EEGX_REQUIRE(eegx::aligned16(part) && eegx::aligned16(dst), EEGX_ERR_ALIGN, "accumulate_partials: 16-byte alignment");
-    accumulate_partials_kernel<<<ew_grid(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(part, (int)s, n / 4, dst,
+    eegx::launch(accumulate_partials_kernel, ew_grid(n / 4), 256, 0, static_cast<cudaStream_t>(stream), part, (int)s, n / 4, dst,
                                                                                               accumulate);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
@@ -612,7 +631,7 @@ int eegx_accumulate_conv_wgrad_f32(const float* part, int64_t s, int64_t Cout, i
     const long long n = Cout * Cin * k;
     if (n == 0) return EEGX_OK;
     EEGX_REQUIRE(part && dst, EEGX_ERR_ARG, "accumulate_conv_wgrad: NULL pointer");
-    accumulate_conv_wgrad_kernel<<<ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(part, (int)s, n, (int)Cin, (int)k,
+    eegx::launch(accumulate_conv_wgrad_kernel, ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream), part, (int)s, n, (int)Cin, (int)k,
                                                                                           dst, accumulate);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
@@ -630,8 +649,8 @@ int eegx_colsum_bf16(const void* y, int64_t ld, int64_t rows, int64_t C, float* 
     const int slabs = slabs_for(g.M, (int)C);
     float* part = static_cast<float*>(workspace);
     dim3 grid((unsigned)((C + CR_COLS - 1) / CR_COLS), (unsigned)slabs);
-    colsum_partial_kernel<<<grid, CR_THREADS, 0, st>>>(static_cast<const __nv_bfloat16*>(y), ld, g, (int)C, part);
-    sum_partials_kernel<<<dim3((unsigned)((C + 31) / 32), 1), 256, 0, st>>>(part, slabs, 1, (int)C, out, accumulate);
+    eegx::launch(colsum_partial_kernel, grid, CR_THREADS, 0, st, static_cast<const __nv_bfloat16*>(y), ld, g, (int)C, part);
+    eegx::launch(sum_partials_kernel, dim3((unsigned)((C + 31) / 32), 1), 256, 0, st, part, slabs, 1, (int)C, out, accumulate);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
 }
@@ -649,7 +668,7 @@ int eegx_bn_act_fwd_bf16(const void* ya, const float* mean_a, const float* rstd_
     const BnSide a{static_cast<const __nv_bfloat16*>(ya), mean_a, rstd_a, gamma_a, beta_a};
     const BnSide r{static_cast<const __nv_bfloat16*>(yr), mean_r, rstd_r, gamma_r, beta_r};
     const DropoutCfg dc{reinterpret_cast<const unsigned long long*>(rng_state), site, p};
-    bn_act_fwd_kernel<<<ew_grid((g.M + 2 * pad) * (C / 8)), 256, 0, st>>>(a, r, res_mode, static_cast<__nv_bfloat16*>(out),
+    eegx::launch(bn_act_fwd_kernel, ew_grid((g.M + 2 * pad) * (C / 8)), 256, 0, st, a, r, res_mode, static_cast<__nv_bfloat16*>(out),
                                                                           g, (int)pad, (int)C, dc);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
@@ -675,10 +694,10 @@ int eegx_bn_act_bwd_bf16(const void* dout, const void* ya, const float* mean_a, 
     const int slabs = slabs_for(g.M, (int)C);
     float* part = static_cast<float*>(workspace);
     dim3 grid((unsigned)((C + CR_COLS - 1) / CR_COLS), (unsigned)slabs);
-    bn_act_bwd_reduce_kernel<<<grid, CR_THREADS, 0, st>>>(a, r, res_mode, static_cast<const __nv_bfloat16*>(dout), g,
+    eegx::launch(bn_act_bwd_reduce_kernel, grid, CR_THREADS, 0, st, a, r, res_mode, static_cast<const __nv_bfloat16*>(dout), g,
                                                           (int)C, dc, part);
-    sum_partials_kernel<<<dim3((unsigned)((C + 31) / 32), 3), 256, 0, st>>>(part, slabs, 3, (int)C, sums);
-    bn_act_bwd_apply_kernel<<<ew_grid((g.M + 2 * pad) * (C / 2)), 256, 0, st>>>(
+    eegx::launch(sum_partials_kernel, dim3((unsigned)((C + 31) / 32), 3), 256, 0, st, part, slabs, 3, (int)C, sums, 0);
+    eegx::launch(bn_act_bwd_apply_kernel, ew_grid((g.M + 2 * pad) * (C / 2)), 256, 0, st, 
         a, r, res_mode, static_cast<const __nv_bfloat16*>(dout), sums, 1.0f / (float)((double)B * (double)T), train,
         static_cast<__nv_bfloat16*>(da), static_cast<__nv_bfloat16*>(dr), g, (int)pad, (int)C, dc);
     EEGX_CUDA_CHECK(cudaGetLastError());
@@ -690,7 +709,7 @@ int eegx_dwconv5_fwd_bf16(const void* x, const float* w, const float* bias, void
     EEGX_GEOM_CHECK("dwconv5_fwd");
     if (B == 0) return EEGX_OK;
     EEGX_REQUIRE(x && w && bias && out, EEGX_ERR_ARG, "dwconv5_fwd: NULL pointer");
-    dwconv5_fwd_kernel<<<ew_grid((g.M + 2 * pad) * (C / 8)), 256, 0, st>>>(
+    eegx::launch(dwconv5_fwd_kernel, ew_grid((g.M + 2 * pad) * (C / 8)), 256, 0, st, 
         static_cast<const __nv_bfloat16*>(x), w, bias, static_cast<__nv_bfloat16*>(out), g, (int)pad, (int)C);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
@@ -704,14 +723,14 @@ int eegx_dwconv5_bwd_bf16(const void* dout, const void* x, const float* w, void*
     if (B == 0) return EEGX_OK;
     EEGX_REQUIRE(dout && x && w && dx && dwdb_scratch && workspace, EEGX_ERR_ARG, "dwconv5_bwd: NULL pointer");
     EEGX_REQUIRE(workspace_bytes >= eegx_colreduce_workspace_bytes(C), EEGX_ERR_WORKSPACE, "dwconv5_bwd: workspace too small");
-    dwconv5_bwd_data_kernel<<<ew_grid((g.M + 2 * pad) * (C / 8)), 256, 0, st>>>(
+    eegx::launch(dwconv5_bwd_data_kernel, ew_grid((g.M + 2 * pad) * (C / 8)), 256, 0, st, 
         static_cast<const __nv_bfloat16*>(dout), w, static_cast<__nv_bfloat16*>(dx), g, (int)pad, (int)C);
     const int slabs = slabs_for(g.M, (int)C);
     float* part = static_cast<float*>(workspace);
     dim3 grid((unsigned)((C + CR_COLS - 1) / CR_COLS), (unsigned)slabs);
-    dwconv5_bwd_weight_kernel<<<grid, CR_THREADS, 0, st>>>(static_cast<const __nv_bfloat16*>(dout),
+    eegx::launch(dwconv5_bwd_weight_kernel, grid, CR_THREADS, 0, st, static_cast<const __nv_bfloat16*>(dout),
                                                            static_cast<const __nv_bfloat16*>(x), g, (int)C, part);
-    sum_partials_kernel<<<dim3((unsigned)((C + 31) / 32), 6), 256, 0, st>>>(part, slabs, 6, (int)C, dwdb_scratch);
+    eegx::launch(sum_partials_kernel, dim3((unsigned)((C + 31) / 32), 6), 256, 0, st, part, slabs, 6, (int)C, dwdb_scratch, 0);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
 }
@@ -721,7 +740,7 @@ int eegx_group_mean_bf16(const void* x, float* s, int64_t B, int64_t T, int64_t 
     if (B == 0) return EEGX_OK;
     EEGX_REQUIRE(x && s, EEGX_ERR_ARG, "group_mean: NULL pointer");
     dim3 grid((unsigned)((C + CR_COLS - 1) / CR_COLS), (unsigned)B);
-    group_mean_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), s, g.Tp, g.lo, g.hi, (int)C);
+    eegx::launch(group_mean_kernel, grid, 256, 0, st, static_cast<const __nv_bfloat16*>(x), s, g.Tp, g.lo, g.hi, (int)C);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
 }
@@ -731,7 +750,7 @@ int eegx_group_mean_bwd_bf16(const float* ds, void* dx, int64_t B, int64_t T, in
     EEGX_GEOM_CHECK("group_mean_bwd");
     if (B == 0) return EEGX_OK;
     EEGX_REQUIRE(ds && dx, EEGX_ERR_ARG, "group_mean_bwd: NULL pointer");
-    group_mean_bwd_kernel<<<ew_grid(B * T * (C / 8)), 256, 0, st>>>(ds, static_cast<__nv_bfloat16*>(dx), B, (int)T, g.Tp,
+    eegx::launch(group_mean_bwd_kernel, ew_grid(B * T * (C / 8)), 256, 0, st, ds, static_cast<__nv_bfloat16*>(dx), B, (int)T, g.Tp,
                                                                     g.lo, (int)C, accumulate);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
@@ -743,7 +762,7 @@ int eegx_se_scale_fwd_bf16(const void* x, const float* e, void* out, int64_t B, 
     if (B == 0) return EEGX_OK;
     EEGX_REQUIRE(x && e && out, EEGX_ERR_ARG, "se_scale_fwd: NULL pointer");
     const DropoutCfg dc{reinterpret_cast<const unsigned long long*>(rng_state), site, p};
-    se_scale_fwd_kernel<<<ew_grid(B * T * (C / 8)), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), e,
+    eegx::launch(se_scale_fwd_kernel, ew_grid(B * T * (C / 8)), 256, 0, st, static_cast<const __nv_bfloat16*>(x), e,
                                                                   static_cast<__nv_bfloat16*>(out), B, (int)T, g.Tp, g.lo,
                                                                   (int)C, dc);
     EEGX_CUDA_CHECK(cudaGetLastError());
@@ -758,11 +777,11 @@ int eegx_se_scale_bwd_bf16(const void* dout, const void* x, const float* e, void
     if (B == 0) return EEGX_OK;
     EEGX_REQUIRE(dout && x && e && dx && de, EEGX_ERR_ARG, "se_scale_bwd: NULL pointer");
     const DropoutCfg dc{reinterpret_cast<const unsigned long long*>(rng_state), site, p};
-    se_scale_bwd_x_kernel<<<ew_grid(B * T * (C / 8)), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dout), e,
+    eegx::launch(se_scale_bwd_x_kernel, ew_grid(B * T * (C / 8)), 256, 0, st, static_cast<const __nv_bfloat16*>(dout), e,
                                                                     static_cast<__nv_bfloat16*>(dx), B, (int)T, g.Tp,
                                                                     g.lo, (int)C, dc);
     dim3 grid((unsigned)((C + CR_COLS - 1) / CR_COLS), (unsigned)B);
-    se_scale_bwd_e_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dout),
+    eegx::launch(se_scale_bwd_e_kernel, grid, 256, 0, st, static_cast<const __nv_bfloat16*>(dout),
                                                 static_cast<const __nv_bfloat16*>(x), de, (int)T, g.Tp, g.lo, (int)C, dc);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
@@ -776,10 +795,10 @@ int eegx_nct_to_rows_bf16(const float* x, int64_t x_bstride, void* out, int64_t 
     if (B == 0) return EEGX_OK;
     EEGX_REQUIRE(x && out, EEGX_ERR_ARG, "nct_to_rows: NULL pointer");
     EEGX_REQUIRE(B <= 65535, EEGX_ERR_SHAPE, "nct_to_rows: B must be <= 65535");
-    zero_invalid_rows_kernel<<<ew_grid((g.M + 2 * pad) * (C / 8)), 256, 0, st>>>(static_cast<__nv_bfloat16*>(out), g,
+    eegx::launch(zero_invalid_rows_kernel, ew_grid((g.M + 2 * pad) * (C / 8)), 256, 0, st, static_cast<__nv_bfloat16*>(out), g,
                                                                                   (int)pad, (int)C);
     dim3 grid((unsigned)((C + TR_C - 1) / TR_C), (unsigned)((T + TR_T - 1) / TR_T), (unsigned)B);
-    nct_to_rows_kernel<<<grid, 256, 0, st>>>(x, x_bstride, static_cast<__nv_bfloat16*>(out), (int)T, g.Tp, g.lo, (int)C);
+    eegx::launch(nct_to_rows_kernel, grid, 256, 0, st, x, x_bstride, static_cast<__nv_bfloat16*>(out), (int)T, g.Tp, g.lo, (int)C);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
 }

@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
               __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
               long long rows, int C, float eps, int act, DropoutCfg dc) {
+    EEGX_PDL_SYNC();
     const int lane = threadIdx.x & 31;
     const long long warp = (long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * LN_WARPS;
@@ -85,6 +86,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
               const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean_in,
               const float* __restrict__ rstd_in, __nv_bfloat16* __restrict__ dx, float* __restrict__ part,
               long long rows, int C, int act, DropoutCfg dc) {
+    EEGX_PDL_SYNC();
     __shared__ float red[LN_WARPS][LN_MAX_C];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const long long warp = (long long)blockIdx.x * LN_WARPS + wid;
@@ -167,6 +169,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
 __global__ void __launch_bounds__(256)
 colsum_partials_kernel(const float* __restrict__ part, int nblocks, int nvec, int C,
                        float* __restrict__ out0, float* __restrict__ out1, int accumulate) {
+    EEGX_PDL_SYNC();
     __shared__ float red[8][32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + lane, j = blockIdx.y;
@@ -190,6 +193,7 @@ colsum_partials_kernel(const float* __restrict__ part, int nblocks, int nvec, in
 __global__ void __launch_bounds__(256)
 add_dropout_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
                        __nv_bfloat16* __restrict__ out, long long n8, float scale, DropoutCfg dc) {
+    EEGX_PDL_SYNC();
     const DropoutGen gen(dc);
     for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n8; g += (long long)gridDim.x * blockDim.x) {
         float av[8], bv[8], m[8], o[8];
@@ -205,6 +209,7 @@ add_dropout_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16*
 __global__ void __launch_bounds__(256)
 dropout_scale_kernel(const __nv_bfloat16* __restrict__ din, __nv_bfloat16* __restrict__ dout, long long n8,
                      float scale, DropoutCfg dc) {
+    EEGX_PDL_SYNC();
     const DropoutGen gen(dc);
     for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n8; g += (long long)gridDim.x * blockDim.x) {
         float v[8], m[8], o[8];
@@ -219,6 +224,7 @@ dropout_scale_kernel(const __nv_bfloat16* __restrict__ din, __nv_bfloat16* __res
 __global__ void __launch_bounds__(256)
 gelu_dropout_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, long long n8,
                         DropoutCfg dc) {
+    EEGX_PDL_SYNC();
     const DropoutGen gen(dc);
     for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n8; g += (long long)gridDim.x * blockDim.x) {
         float v[8], m[8], o[8];
@@ -233,6 +239,7 @@ gelu_dropout_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __re
 __global__ void __launch_bounds__(256)
 gelu_dropout_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ x,
                         __nv_bfloat16* __restrict__ dx, long long n8, DropoutCfg dc) {
+    EEGX_PDL_SYNC();
     const DropoutGen gen(dc);
     for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n8; g += (long long)gridDim.x * blockDim.x) {
         float v[8], d[8], m[8], o[8];
@@ -249,6 +256,7 @@ gelu_dropout_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloa
 __global__ void __launch_bounds__(256)
 glu_fwd_kernel(const __nv_bfloat16* __restrict__ ag, __nv_bfloat16* __restrict__ out, long long rows, int H,
                DropoutCfg dc) {
+    EEGX_PDL_SYNC();
     const DropoutGen gen(dc);
     const int h8 = H >> 3;
     const long long n8 = rows * h8;
@@ -268,6 +276,7 @@ glu_fwd_kernel(const __nv_bfloat16* __restrict__ ag, __nv_bfloat16* __restrict__
 __global__ void __launch_bounds__(256)
 glu_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ ag,
                __nv_bfloat16* __restrict__ dag, long long rows, int H, DropoutCfg dc) {
+    EEGX_PDL_SYNC();
     const DropoutGen gen(dc);
     const int h8 = H >> 3;
     const long long n8 = rows * h8;
@@ -309,7 +318,7 @@ int ln_grid(long long rows, bool bwd) {
 template <int NVEC>
 void launch_ln_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                    long long rows, int C, float eps, int act, DropoutCfg dc, cudaStream_t st) {
-    ln_fwd_kernel<NVEC><<<ln_grid(rows, false), LN_WARPS * 32, 0, st>>>(
+    eegx::launch(ln_fwd_kernel<NVEC>, ln_grid(rows, false), LN_WARPS * 32, 0, st, 
         static_cast<const __nv_bfloat16*>(x), gamma, beta, static_cast<__nv_bfloat16*>(y), mean, rstd, rows, C, eps,
         act, dc);
 }
@@ -318,7 +327,7 @@ template <int NVEC>
 void launch_ln_bwd(const void* dy, const void* x, const float* gamma, const float* beta, const float* mean,
                    const float* rstd, void* dx, float* part, int grid, long long rows, int C, int act,
                    DropoutCfg dc, cudaStream_t st) {
-    ln_bwd_kernel<NVEC><<<grid, LN_WARPS * 32, 0, st>>>(
+    eegx::launch(ln_bwd_kernel<NVEC>, grid, LN_WARPS * 32, 0, st, 
         static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), gamma, beta, mean, rstd,
         static_cast<__nv_bfloat16*>(dx), part, rows, C, act, dc);
 }
@@ -386,7 +395,7 @@ int eegx_layernorm_bwd_bf16(const void* dy, const void* x, const float* gamma, c
         case 5: case 6: launch_ln_bwd<6>(dy, x, gamma, beta, mean, rstd, dx, part, grid, rows, (int)C, act, dc, st); break;
         default: launch_ln_bwd<8>(dy, x, gamma, beta, mean, rstd, dx, part, grid, rows, (int)C, act, dc, st); break;
     }
-    colsum_partials_kernel<<<dim3((unsigned)((C + 31) / 32), 2), 256, 0, st>>>(part, grid, 2, (int)C, dgamma, dbeta, accumulate);
+    eegx::launch(colsum_partials_kernel, dim3((unsigned)((C + 31) / 32), 2), 256, 0, st, part, grid, 2, (int)C, dgamma, dbeta, accumulate);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
 }
@@ -399,7 +408,7 @@ int eegx_add_dropout_fwd_bf16(const void* a, const void* b, void* out, int64_t n
     EEGX_REQUIRE(eegx::aligned16(a) && eegx::aligned16(b) && eegx::aligned16(out), EEGX_ERR_ALIGN,
                  "add_dropout: pointers must be 16-byte aligned");
     const DropoutCfg dc{reinterpret_cast<const unsigned long long*>(rng_state), site, p};
-    add_dropout_fwd_kernel<<<ew_grid(n / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    eegx::launch(add_dropout_fwd_kernel, ew_grid(n / 8), 256, 0, static_cast<cudaStream_t>(stream), 
         static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b), static_cast<__nv_bfloat16*>(out),
         n / 8, scale, dc);
     EEGX_CUDA_CHECK(cudaGetLastError());
@@ -414,7 +423,7 @@ int eegx_dropout_scale_bf16(const void* in, void* out, int64_t n, float scale, c
     EEGX_REQUIRE(eegx::aligned16(in) && eegx::aligned16(out), EEGX_ERR_ALIGN,
                  "dropout_scale: pointers must be 16-byte aligned");
     const DropoutCfg dc{reinterpret_cast<const unsigned long long*>(rng_state), site, p};
-    dropout_scale_kernel<<<ew_grid(n / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    eegx::launch(dropout_scale_kernel, ew_grid(n / 8), 256, 0, static_cast<cudaStream_t>(stream), 
         static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), n / 8, scale, dc);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
@@ -428,7 +437,7 @@ int eegx_gelu_dropout_fwd_bf16(const void* x, void* out, int64_t n, const uint64
     EEGX_REQUIRE(eegx::aligned16(x) && eegx::aligned16(out), EEGX_ERR_ALIGN,
                  "gelu_dropout: pointers must be 16-byte aligned");
     const DropoutCfg dc{reinterpret_cast<const unsigned long long*>(rng_state), site, p};
-    gelu_dropout_fwd_kernel<<<ew_grid(n / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    eegx::launch(gelu_dropout_fwd_kernel, ew_grid(n / 8), 256, 0, static_cast<cudaStream_t>(stream), 
         static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), n / 8, dc);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
@@ -442,7 +451,7 @@ int eegx_gelu_dropout_bwd_bf16(const void* dout, const void* x, void* dx, int64_
     EEGX_REQUIRE(eegx::aligned16(dout) && eegx::aligned16(x) && eegx::aligned16(dx), EEGX_ERR_ALIGN,
                  "gelu_dropout bwd: pointers must be 16-byte aligned");
     const DropoutCfg dc{reinterpret_cast<const unsigned long long*>(rng_state), site, p};
-    gelu_dropout_bwd_kernel<<<ew_grid(n / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    eegx::launch(gelu_dropout_bwd_kernel, ew_grid(n / 8), 256, 0, static_cast<cudaStream_t>(stream), 
         static_cast<const __nv_bfloat16*>(dout), static_cast<const __nv_bfloat16*>(x),
         static_cast<__nv_bfloat16*>(dx), n / 8, dc);
     EEGX_CUDA_CHECK(cudaGetLastError());
@@ -457,7 +466,7 @@ int eegx_glu_fwd_bf16(const void* ag, void* out, int64_t rows, int64_t H, const 
     EEGX_REQUIRE(ag && out, EEGX_ERR_ARG, "glu: NULL pointer");
     EEGX_REQUIRE(eegx::aligned16(ag) && eegx::aligned16(out), EEGX_ERR_ALIGN, "glu: pointers must be 16-byte aligned");
     const DropoutCfg dc{reinterpret_cast<const unsigned long long*>(rng_state), site, p};
-    glu_fwd_kernel<<<ew_grid(rows * (H / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    eegx::launch(glu_fwd_kernel, ew_grid(rows * (H / 8)), 256, 0, static_cast<cudaStream_t>(stream), 
         static_cast<const __nv_bfloat16*>(ag), static_cast<__nv_bfloat16*>(out), rows, (int)H, dc);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
@@ -472,7 +481,7 @@ int eegx_glu_bwd_bf16(const void* dout, const void* ag, void* dag, int64_t rows,
     EEGX_REQUIRE(eegx::aligned16(dout) && eegx::aligned16(ag) && eegx::aligned16(dag), EEGX_ERR_ALIGN,
                  "glu bwd: pointers must be 16-byte aligned");
     const DropoutCfg dc{reinterpret_cast<const unsigned long long*>(rng_state), site, p};
-    glu_bwd_kernel<<<ew_grid(rows * (H / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    eegx::launch(glu_bwd_kernel, ew_grid(rows * (H / 8)), 256, 0, static_cast<cudaStream_t>(stream), 
         static_cast<const __nv_bfloat16*>(dout), static_cast<const __nv_bfloat16*>(ag),
         static_cast<__nv_bfloat16*>(dag), rows, (int)H, dc);
     EEGX_CUDA_CHECK(cudaGetLastError());

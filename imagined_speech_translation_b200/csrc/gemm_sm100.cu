@@ -329,6 +329,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const GemmParams p) {
     using L = SmemLayout<BLOCK_N, STAGES>;
+    EEGX_PDL_TRIGGER();        // the next kernel's CTAs may be scheduled behind this grid's
     extern __shared__ unsigned char smem_raw[];
     // 1024-byte alignment required by the 128B swizzle atoms
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -367,6 +368,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const unsigned tmem_base = *tmem_ptr_smem;
+    EEGX_PDL_WAIT();           // barrier init, TMEM allocation and descriptor prefetch above overlap the previous kernel's tail
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -728,7 +730,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, in
     using L = SmemLayout<BLOCK_N, STAGES>;
     auto kern = gemm_bf16_kernel<BLOCK_N, STAGES, A_MN, B_MN>;
     EEGX_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(ma, mb, p);
+    EEGX_CUDA_CHECK(eegx::launch(kern, grid, NUM_THREADS, L::TOTAL, st, ma, mb, p));
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
 }

@@ -33,6 +33,7 @@ __device__ __forceinline__ void online_merge(float& m, float& s, float m2, float
 __global__ void __launch_bounds__(CE_THREADS)
 ce_fwd_kernel(const __nv_bfloat16* __restrict__ logits, long long ld, const long long* __restrict__ labels,
               long long V, long long ignore_index, float* __restrict__ loss_rows, float* __restrict__ lse_out) {
+    EEGX_PDL_SYNC();
     __shared__ float sm[CE_THREADS / 32], ss[CE_THREADS / 32];
     const long long r = blockIdx.x;
     const __nv_bfloat16* row = logits + r * ld;
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(CE_THREADS)
 ce_bwd_kernel(const __nv_bfloat16* __restrict__ logits, long long ld, const long long* __restrict__ labels,
               const float* __restrict__ lse, const float* __restrict__ coef, __nv_bfloat16* __restrict__ dlogits,
               long long V, long long ignore_index) {
+    EEGX_PDL_SYNC();
     const long long r = blockIdx.x;
     const __nv_bfloat16* row = logits + r * ld;
     __nv_bfloat16* drow = dlogits + r * ld;
@@ -98,7 +100,7 @@ int eegx_ce_fwd_bf16(const void* logits, int64_t ld, const int64_t* labels, int6
     if (rows == 0) return EEGX_OK;
     EEGX_REQUIRE(logits && labels && loss_rows && lse, EEGX_ERR_ARG, "cross-entropy: NULL pointer");
     EEGX_REQUIRE(eegx::aligned16(logits), EEGX_ERR_ALIGN, "cross-entropy: logits must be 16-byte aligned");
-    ce_fwd_kernel<<<(unsigned)rows, CE_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+    eegx::launch(ce_fwd_kernel, (unsigned)rows, CE_THREADS, 0, static_cast<cudaStream_t>(stream), 
         static_cast<const __nv_bfloat16*>(logits), ld, reinterpret_cast<const long long*>(labels), V, ignore_index,
         loss_rows, lse);
     EEGX_CUDA_CHECK(cudaGetLastError());
@@ -114,7 +116,7 @@ int eegx_ce_bwd_bf16(const void* logits, int64_t ld, const int64_t* labels, cons
     EEGX_REQUIRE(logits && labels && lse && coef && dlogits, EEGX_ERR_ARG, "cross-entropy bwd: NULL pointer");
     EEGX_REQUIRE(eegx::aligned16(logits) && eegx::aligned16(dlogits), EEGX_ERR_ALIGN,
                  "cross-entropy bwd: logits / dlogits must be 16-byte aligned");
-    ce_bwd_kernel<<<(unsigned)rows, CE_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+    eegx::launch(ce_bwd_kernel, (unsigned)rows, CE_THREADS, 0, static_cast<cudaStream_t>(stream), 
         static_cast<const __nv_bfloat16*>(logits), ld, reinterpret_cast<const long long*>(labels), lse, coef,
         static_cast<__nv_bfloat16*>(dlogits), V, ignore_index);
     EEGX_CUDA_CHECK(cudaGetLastError());

@@ -35,6 +35,7 @@ normalize_vec4_kernel(const float* __restrict__ x, const int32_t* __restrict__ c
                       float* __restrict__ out, const int64_t* __restrict__ out_off,
                       const int64_t* __restrict__ out_bstride, int64_t rows, int C_in, int C_out,
                       int T4) {
+    EEGX_PDL_SYNC();
     const int chunks_per_row = (T4 + 256 * UNROLL - 1) / (256 * UNROLL);
     const int64_t total_chunks = rows * chunks_per_row;
     for (int64_t chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
@@ -78,6 +79,7 @@ normalize_scalar_kernel(const float* __restrict__ x, const int32_t* __restrict__
                         float* __restrict__ out, const int64_t* __restrict__ out_off,
                         const int64_t* __restrict__ out_bstride, int64_t rows, int C_in, int C_out,
                         int T) {
+    EEGX_PDL_SYNC();
     for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
         const int64_t b = row / C_out;
         const int j = (int)(row - b * C_out);
@@ -119,6 +121,7 @@ zscore_time_kernel(const float* __restrict__ x, const int32_t* __restrict__ ch_i
                    float* __restrict__ out, const int64_t* __restrict__ out_off,
                    const int64_t* __restrict__ out_bstride, int64_t rows, int C_in, int C_out,
                    int T) {
+    EEGX_PDL_SYNC();
     extern __shared__ float row_s[];
     __shared__ float red[33];
     for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
@@ -183,13 +186,13 @@ extern "C" int eegx_normalize_f32(const float* x, const int32_t* ch_idx, const f
         const int64_t total = rows * chunks_per_row;
         const int grid = (int)(total < (int64_t)eegx::kNumSMsB200 * 32 ? total
                                                                         : (int64_t)eegx::kNumSMsB200 * 32);
-        normalize_vec4_kernel<UNROLL><<<grid, 256, 0, st>>>(x, ch_idx, center, scale, out, out_off,
+        eegx::launch(normalize_vec4_kernel<UNROLL>, grid, 256, 0, st, x, ch_idx, center, scale, out, out_off,
                                                             out_bstride, rows, (int)C_in, (int)C_out,
                                                             T4);
     } else {
         const int grid = (int)(rows < (int64_t)eegx::kNumSMsB200 * 16 ? rows
                                                                        : (int64_t)eegx::kNumSMsB200 * 16);
-        normalize_scalar_kernel<<<grid, 256, 0, st>>>(x, ch_idx, center, scale, out, out_off,
+        eegx::launch(normalize_scalar_kernel, grid, 256, 0, st, x, ch_idx, center, scale, out, out_off,
                                                       out_bstride, rows, (int)C_in, (int)C_out,
                                                       (int)T);
     }
@@ -216,7 +219,7 @@ extern "C" int eegx_zscore_time_f32(const float* x, const int32_t* ch_idx, float
         EEGX_CUDA_CHECK(cudaFuncSetAttribute(zscore_time_kernel,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (int)(rows < (int64_t)eegx::kNumSMsB200 * 8 ? rows : (int64_t)eegx::kNumSMsB200 * 8);
-    zscore_time_kernel<<<grid, 256, smem, st>>>(x, ch_idx, out, out_off, out_bstride, rows,
+    eegx::launch(zscore_time_kernel, grid, 256, smem, st, x, ch_idx, out, out_off, out_bstride, rows,
                                                 (int)C_in, (int)C_out, (int)T);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;

@@ -26,6 +26,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // stage 1: one partial per CTA (fixed grid => fixed summation order => bit-stable)
 __global__ void __launch_bounds__(NT) sumsq_partial_kernel(const float* __restrict__ g, long long n,
                                                            double* __restrict__ partials) {
+    EEGX_PDL_SYNC();
     __shared__ float red[NT / 32];
     float acc = 0.0f;
     const long long n4 = n >> 2;
@@ -48,6 +49,7 @@ __global__ void __launch_bounds__(NT) sumsq_partial_kernel(const float* __restri
 
 // stage 2: single warp, fixed order, fp64; out[0] (+)= sum
 __global__ void sumsq_final_kernel(const double* __restrict__ partials, int count, float* out, int accumulate) {
+    EEGX_PDL_SYNC();
     double acc = 0.0;
     for (int i = threadIdx.x; i < count; i += 32) acc += partials[i];
 #pragma unroll
@@ -59,6 +61,7 @@ __global__ void __launch_bounds__(NT)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              long long n, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt,
              const float* __restrict__ norm_sq, float max_norm, float grad_scale, __nv_bfloat16* __restrict__ w16) {
+    EEGX_PDL_SYNC();
     // clip coefficient of clip_grad_norm_: min(1, max_norm / (||g|| + 1e-6)); grads may carry a
     // constant factor (grad_scale, e.g. 1/world_size) that is folded in here.
     float coef = grad_scale;
@@ -119,8 +122,8 @@ extern "C" int eegx_sumsq_f32(const float* g, int64_t n, float* out, int accumul
     long long blocks = (n / 4 + NT - 1) / NT;
     if (blocks < 1) blocks = 1;
     if (blocks > MAX_PARTIALS) blocks = MAX_PARTIALS;
-    sumsq_partial_kernel<<<(int)blocks, NT, 0, st>>>(g, n, static_cast<double*>(workspace));
-    sumsq_final_kernel<<<1, 32, 0, st>>>(static_cast<const double*>(workspace), (int)blocks, out, accumulate);
+    eegx::launch(sumsq_partial_kernel, (int)blocks, NT, 0, st, g, n, static_cast<double*>(workspace));
+    eegx::launch(sumsq_final_kernel, 1, 32, 0, st, static_cast<const double*>(workspace), (int)blocks, out, accumulate);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
 }
@@ -140,7 +143,7 @@ extern "C" int eegx_adamw_clip_f32(float* p, const float* g, float* m, float* v,
     long long blocks = (n / 4 + NT - 1) / NT;
     if (blocks < 1) blocks = 1;
     if (blocks > eegx::kNumSMsB200 * 8) blocks = eegx::kNumSMsB200 * 8;
-    adamw_kernel<<<(int)blocks, NT, 0, static_cast<cudaStream_t>(stream)>>>(
+    eegx::launch(adamw_kernel, (int)blocks, NT, 0, static_cast<cudaStream_t>(stream), 
         p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, grad_norm_sq, max_norm, grad_scale,
         static_cast<__nv_bfloat16*>(w16));
     EEGX_CUDA_CHECK(cudaGetLastError());
