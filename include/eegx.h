@@ -319,6 +319,28 @@ int eegx_region_std_f32(const float* x, int64_t B, int64_t n, float* out, void* 
 int eegx_augment_f32(const float* x, float* out, int64_t B, int64_t C, int64_t T, const float* sigma,
                      const float* scale, const int32_t* shift, const uint64_t* rng_state, uint32_t site, void* stream);
 
+/* ------------------------------------------------------------------------
+ * wake_model dense head (BASELINE config 5): Linear(in, hidden, act) -> Linear(hidden, n_cls, softmax) ->
+ * categorical cross-entropy, per-sample SGD in fp64, n samples IN ORDER in one persistent cooperative launch.
+ *
+ * Replaces wake_model/layers/linear.cpp:5-44 (Linear::forward), :47-72 (Linear::backward with the in-place SGD
+ * update), layers/activations.h:29-41,64-95, layers/losses.h:8-22 and the Linear part of the loop
+ * wake_model/train.cpp:68-117.
+ *   w1 (hidden, in), b1 (hidden), w2 (n_cls, hidden), b2 (n_cls): fp64 device buffers, updated in place (train = 1).
+ *   x (n, in) fp64, label (n) int32 class index (train.cpp:102 one-hot position).
+ *   activation: 0 none, 1 relu, 2 sigmoid, 3 tanh (hidden layer; derivative taken at the layer OUTPUT as the
+ *   reference does).  train = 0: forward only (loss / probs), no updates.
+ *   loss (n), probs (n, n_cls), dx (n, in; = what Linear::backward of the hidden layer returns): nullable outputs.
+ *   Needs about 2*in + n_cls*(ceil(hidden/SMs) + 3) doubles of shared memory (<= 227 KB), else EEGX_ERR_SHAPE.
+ * Tolerance vs the reference: the SGD update itself is rounded exactly as the C++ (mul, mul, sub); dot products
+ * are summed in a different fixed order -> parameters agree to ~1e-10 relative after tens of samples.
+ * ------------------------------------------------------------------------ */
+size_t eegx_wake_dense_workspace_bytes(int64_t in, int64_t hidden, int64_t n_cls, int want_dx);
+int eegx_wake_dense_f64(double* w1, double* b1, double* w2, double* b2, const double* x, const int32_t* label,
+                        int64_t n, int64_t in, int64_t hidden, int64_t n_cls, double lr, int activation, int train,
+                        double* loss, double* probs, double* dx, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif
