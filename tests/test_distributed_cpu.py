@@ -38,7 +38,8 @@ def _worker(rank, world, port, q):
     flat = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None])
     buf = [flat.clone()]
     dp.allreduce_sum_(buf)                                   # flat-buffer path: SUM
-    q.put((rank, flat, calls, buf[0], [p.grad is None for p in model.parameters()]))
+    # numpy arrays travel by value; tensors would travel as shared-memory handles that die with this process
+    q.put((rank, flat.numpy().copy(), calls, buf[0].numpy().copy(), [p.grad is None for p in model.parameters()]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -50,6 +51,7 @@ def test_gradient_allreduce_matches_full_batch():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     [p.start() for p in procs]
     res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    res = [(r, torch.from_numpy(f), c, torch.from_numpy(b), n) for r, f, c, b, n in res]
     [p.join(timeout=60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     # single-process reference on the full batch
