@@ -200,8 +200,9 @@ def workload_config(workload, extra=None):
                            "BART decoder + LM head + CE, clip + AdamW), bf16 tensor cores / fp32 master weights, "
                            "batch 256 per GPU, data-parallel",
                "model_params": 0, "tokens_per_trial": L_TOK, "accumulation_steps": 1, "dropout": "on (train mode)",
-               "execution": "preprocess + forward + backward replayed as one CUDA graph; all-reduce + fused clip/AdamW "
-                            "launched after it"}
+               "execution": "preprocess + forward + backward replayed as one CUDA graph; at N > 1 the graph also holds "
+                            "the NCCL all-reduces of the flat gradient buffer, issued slice by slice from inside "
+                            "backward (89 % of the bytes overlap it); fused clip/AdamW launched after the graph"}
     cfg.update({"batch_per_gpu": B_PER_GPU, "channels": C, "samples": T, "n_fft": N_FFT, "hop": HOP,
                 "l2": "working set per step (>= 413 MB of trial + feature tensors) exceeds the 126 MB L2; "
                       "2 rotating input buffers"})
@@ -294,6 +295,9 @@ def run_ours(args, rank, world, local_rank):
             sampler.start()
         dsp = bench_dsp(fe, dev, rank, world, args, barrier)
         clocks = sampler.stop() if sampler else None
+        if world > 1:
+            from imagined_speech_translation_b200 import distributed as dp
+            dp.shutdown()
         if rank == 0:
             cpu_val, cores, sample, _ = time_cpu("dsp", budget_s=10.0)
             print(json.dumps({
@@ -304,8 +308,6 @@ def run_ours(args, rank, world, local_rank):
                 "e2e": None, "gpu_launches": dsp["gpu_launches"], "roofline": dsp["roofline"],
                 "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             }), flush=True)
-        if world > 1:
-            dist.destroy_process_group()
         return
 
     # ---------------- train workload ----------------
@@ -413,7 +415,8 @@ def run_ours(args, rank, world, local_rank):
     # (single stream, so the events bracket exactly one GEMM and nothing runs beside it)
     # and with the GPU kept ~150 ms behind the CPU, so the host-side work of a call -- tensor-map encode,
     # launch -- never shows up between a GEMM's two events)
-    trainer._graph = None
+    trainer.release_graph()
+    trainer.overlap_allreduce = False                          # no NCCL kernels beside the GEMMs being timed
     model.brain_encoder.parallel_regions = False
     step(batches[0])
     torch.cuda.synchronize()
@@ -435,6 +438,10 @@ def run_ours(args, rank, world, local_rank):
     gemm_flops = sum(r[2] for r in rec)
 
     dsp = bench_dsp(fe, dev, rank, world, args, barrier)
+    if world > 1:
+        # all GPU work is done: tear the process group down together, BEFORE rank 0's CPU-baseline leg
+        from imagined_speech_translation_b200 import distributed as dp
+        dp.shutdown(trainer)
 
     if rank == 0:
         _, tf_peak, src = measured_peaks()
@@ -468,8 +475,6 @@ def run_ours(args, rank, world, local_rank):
             "dsp": dsp,
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         }), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def main():

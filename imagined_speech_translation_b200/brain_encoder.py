@@ -124,6 +124,7 @@ class BrainRegionEncoder(nn.Module):
     def forward(self, eeg_data):
         feats = self._region_features(eeg_data)
         x = torch.stack(feats, dim=1)                            # (B, 4, d) fp32
+        x = fused.grad_boundary(x, ('fusion', id(self)))         # everything after the region encoders
         ms = self.apply_multi_scale_processing(x.to(torch.bfloat16))
         x = x + 0.3 * ms.float()
         x = x + 0.4 * self.region_embeddings.weight.unsqueeze(0)
@@ -136,12 +137,12 @@ class BrainRegionEncoder(nn.Module):
                                                 xt.float().mean(dim=1).to(torch.bfloat16)).float()).unsqueeze(1)
             x = xt.float() + gate * xc.float()
         if self.uniform_region_weight or not hasattr(self, 'region_importance'):
-            fused = x.mean(dim=1)
+            pooled = x.mean(dim=1)
         else:
             w = self.compute_dynamic_region_weights(x)
-            fused = (x * w.unsqueeze(-1)).sum(dim=1)
-        enhanced = run_sequential(self.feature_enhancer, fused.to(torch.bfloat16)).float()
-        return fused + 0.3 * enhanced
+            pooled = (x * w.unsqueeze(-1)).sum(dim=1)
+        enhanced = run_sequential(self.feature_enhancer, pooled.to(torch.bfloat16)).float()
+        return pooled + 0.3 * enhanced
 
     def get_region_weights(self):
         """Same report as the reference (brain_encoder.py:195-214)."""

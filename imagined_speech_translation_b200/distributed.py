@@ -84,3 +84,25 @@ def allreduce_gradients(params: Sequence[torch.nn.Parameter], group=None, averag
             flush()
     flush()
     return calls
+
+
+def shutdown(trainer=None, grace_s: float = 30.0) -> None:
+    """Orderly end of a data-parallel job: release captured graphs (they may hold NCCL kernels), barrier,
+    destroy the process group.  A watchdog ends the process with status 0 if the teardown itself stalls
+    (every result has been reported by then) instead of leaving the launcher waiting."""
+    import os
+    import sys
+    import threading
+    sys.stdout.flush()
+    sys.stderr.flush()
+    timer = threading.Timer(grace_s, lambda: os._exit(0))
+    timer.daemon = True
+    timer.start()
+    if trainer is not None:
+        trainer.release_graph()
+    if dist.is_available() and dist.is_initialized():
+        try:
+            dist.barrier()
+        finally:
+            dist.destroy_process_group()
+    timer.cancel()

@@ -572,3 +572,37 @@ def attn_cross(q: torch.Tensor, kv: torch.Tensor, B: int, Sq: int, Sk: int, H: i
     """q: (B*Sq, d), kv: (B*Sk, 2*d) -> (B*Sq, d)."""
     rng, site, p = _drop(p, training, q.device)
     return _AttnCore.apply(q.contiguous(), kv.contiguous(), B, Sq, Sk, H, False, rng, site, p)
+
+
+# ------------------------------------------------------------------------------------------------
+# Gradient-ready boundaries (data-parallel overlap).  An identity in forward; in backward it tells
+# the registered callback that every parameter used DOWNSTREAM of this point has its gradient
+# complete (all those nodes were created later, so autograd ran them first, and our backward
+# functions accumulate weight gradients inside the same node).  trainer.EEGTrainer uses it to
+# start the all-reduce of that slice of the flat gradient buffer while backward continues.
+_BOUNDARY_CB = None
+
+
+def set_grad_boundary_callback(cb):
+    global _BOUNDARY_CB
+    _BOUNDARY_CB = cb
+
+
+class _GradBoundary(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, key):
+        ctx.key = key
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        cb = _BOUNDARY_CB
+        if cb is not None:
+            cb(ctx.key)
+        return g, None
+
+
+def grad_boundary(x, key):
+    if _BOUNDARY_CB is None or not torch.is_grad_enabled() or not x.requires_grad:
+        return x
+    return _GradBoundary.apply(x, key)

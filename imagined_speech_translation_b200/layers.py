@@ -265,6 +265,7 @@ class Conv1DWithAttention(nn.Module):
         if S > pos.size(1):                                     # longer than built for: tile (layers.py:222-225)
             pos = pos.repeat(1, S // pos.size(1) + 1, 1)
         h = (h + pos[:, :S]).to(torch.bfloat16)                 # bf16 + fp32 -> fp32 add, one rounding
+        h = fused.grad_boundary(h, ('region', id(self)))        # attention stack + heads: gradients final here
 
         prev = None
         for i, layer in enumerate(self.attn_layers):

@@ -136,8 +136,8 @@ class EEGDecodingModel(nn.Module):
         self.bart_decoder = BARTDecoder(hidden_dim=hidden_dim)
 
     def forward(self, eeg_data, decoder_input_ids=None, labels=None, **kwargs):
-        return self.bart_decoder(eeg_feat=self.brain_encoder(eeg_data), decoder_input_ids=decoder_input_ids,
-                                 labels=labels, **kwargs)
+        feat = fused.grad_boundary(self.brain_encoder(eeg_data), ('decoder', id(self.bart_decoder)))
+        return self.bart_decoder(eeg_feat=feat, decoder_input_ids=decoder_input_ids, labels=labels, **kwargs)
 
     def generate(self, eeg_data, **kwargs):
         return self.bart_decoder.generate_from_eeg(self.brain_encoder(eeg_data), **kwargs)

@@ -48,6 +48,7 @@ class FlatAdamW(torch.optim.Optimizer):
         dev = next(ps[0].device for ps, _ in plan if ps)
         self._all_grads = torch.zeros(sum(sum(sz) for _, sz in plan), device=dev)
         flats, base = [], 0
+        self._offsets = {}         # id(param) -> (offset, padded length) inside _all_grads
         for ps, sizes in plan:
             if not ps:
                 flats.append(None)
@@ -56,16 +57,17 @@ class FlatAdamW(torch.optim.Optimizer):
             flat_p = torch.zeros(total, device=dev)
             flat_w16 = torch.zeros(total, device=dev, dtype=torch.bfloat16)     # bf16 shadow, kept current by the AdamW kernel
             flat_g = self._all_grads[base:base + total]
-            base += total
             off = 0
             for p, n in zip(ps, sizes):
                 k = p.numel()
+                self._offsets[id(p)] = (base + off, n)
                 flat_p[off:off + k].copy_(p.data.reshape(-1))
                 flat_g[off:off + k].copy_(p.grad.reshape(-1))
                 p.data = flat_p[off:off + k].view_as(p)
                 p.grad = flat_g[off:off + k].view_as(p)
                 p._eegx_w16 = flat_w16[off:off + k].view_as(p)
                 off += n
+            base += total
             flat_w16.copy_(flat_p)
             flats.append(dict(p=flat_p, g=flat_g, m=torch.zeros_like(flat_p), v=torch.zeros_like(flat_p),
                               w16=flat_w16, params=ps))
@@ -79,6 +81,20 @@ class FlatAdamW(torch.optim.Optimizer):
         if self._flat is None:
             self._build()
         return [self._all_grads]
+
+    def grad_runs(self, params):
+        """Contiguous [lo, hi) runs of the flat gradient buffer that hold the gradients of ``params``
+        (parameters without a gradient are skipped), merged where adjacent."""
+        if self._flat is None:
+            self._build()
+        spans = sorted(self._offsets[id(p)] for p in params if id(p) in self._offsets)
+        runs = []
+        for off, n in spans:
+            if runs and runs[-1][1] == off:
+                runs[-1][1] = off + n
+            else:
+                runs.append([off, off + n])
+        return [tuple(r) for r in runs]
 
     def zero_grad(self, set_to_none: bool = False):
         if self._flat is None:

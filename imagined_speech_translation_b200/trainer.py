@@ -15,6 +15,8 @@ from __future__ import annotations
 import math
 from typing import Optional
 
+import os
+
 import torch
 
 from . import distributed as dp
@@ -103,6 +105,13 @@ class EEGTrainer:
         self.process_group = process_group
         self.world_size = torch.distributed.get_world_size(process_group) \
             if torch.distributed.is_initialized() else 1
+        # data-parallel: all-reduce slices of the flat gradient buffer as backward finishes them (EEGX_OVERLAP_ALLREDUCE=0
+        # falls back to one all-reduce after backward)
+        self.overlap_allreduce = os.environ.get('EEGX_OVERLAP_ALLREDUCE', '1') != '0'
+        self._plan = None
+        self._works = []
+        self._grads_reduced = False
+        self._graph_reduces = False
         self.best_bleu4 = 0.0
         self.patience_counter = 0
         self.global_step = 0
@@ -116,14 +125,63 @@ class EEGTrainer:
         return [r.to(self.device, non_blocking=True) for r in batch['eeg']]
 
     def forward_pass(self, eeg, decoder_input_ids, labels):
-        feats = self.model.brain_encoder(eeg)
-        return self.model.bart_decoder(eeg_feat=feats, decoder_input_ids=decoder_input_ids, labels=labels)
+        return self.model(eeg, decoder_input_ids=decoder_input_ids, labels=labels)
+
+    # ------------------------------------------------------------------ all-reduce overlapped with backward
+    def _overlap_plan(self):
+        """Which slices of the flat gradient buffer are final at which point of backward (SURVEY.md 8(e):
+        "bucketed and overlapped with backward").  Backward runs decoder -> fusion stage -> the four region
+        encoders (attention stack, then CNN); a `fused.grad_boundary` sits at each of those transitions and
+        its backward starts the all-reduce of the slice that has just become final.  Only what is left
+        (region CNN stacks, tokens, positions: ~8 % of the bytes) is reduced after backward."""
+        if self._plan is not None:
+            return self._plan
+        opt, model = self.optimizer, self.model
+        enc, dec = model.brain_encoder, model.bart_decoder
+        plan = {('decoder', id(dec)): opt.grad_runs(list(dec.parameters())),
+                ('fusion', id(enc)): opt.grad_runs([p for n, p in enc.named_parameters()
+                                                    if not n.startswith('region_encoders.')])}
+        for m in enc.region_encoders.values():
+            if getattr(m, 'cnn_only', False):
+                continue
+            after = [p for sub in (m.attn_layers, m.cross_scale_attn, m.multi_scale_proj, m.projection,
+                                   m.diversity_head) for p in sub.parameters()]
+            plan[('region', id(m))] = opt.grad_runs(after)
+        covered = sorted(r for runs in plan.values() for r in runs)
+        rest, pos, total = [], 0, opt._all_grads.numel()
+        for lo, hi in covered:
+            if lo < pos:
+                raise RuntimeError("overlap plan: gradient slices overlap")
+            if lo > pos:
+                rest.append((pos, lo))
+            pos = hi
+        if pos < total:
+            rest.append((pos, total))
+        plan['rest'] = rest
+        self._plan = plan
+        return plan
+
+    def _overlap_active(self):
+        return (self.world_size > 1 and self.overlap_allreduce and self.config['accumulation_steps'] == 1
+                and isinstance(self.optimizer, FlatAdamW) and self.optimizer._flat is not None)
+
+    def _reduce_runs(self, runs):
+        g = self.optimizer._all_grads
+        for lo, hi in runs:
+            self._works.append(torch.distributed.all_reduce(g[lo:hi], group=self.process_group, async_op=True))
+
+    def _on_boundary(self, key):
+        runs = self._overlap_plan().get(key)
+        if runs:
+            self._reduce_runs(runs)
 
     def _optimizer_step(self, step_scheduler: bool):
         clip = self.config.get('grad_clip_norm', 1.0)
         if isinstance(self.optimizer, FlatAdamW):
             if self.world_size > 1:
-                dp.allreduce_sum_(self.optimizer.flat_grads(), self.process_group)
+                if not self._grads_reduced:
+                    dp.allreduce_sum_(self.optimizer.flat_grads(), self.process_group)
+                self._grads_reduced = False
                 self.optimizer.grad_scale = 1.0 / self.world_size
             self.optimizer.step(max_grad_norm=clip)
         else:
@@ -151,6 +209,7 @@ class EEGTrainer:
             for _ in range(warmup):
                 self._eager_step(self._static)
             self.optimizer.zero_grad()
+            self._grads_reduced = False
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         from . import nn_ops
@@ -158,19 +217,48 @@ class EEGTrainer:
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self._static_loss = self._eager_step(self._static)
+        self._graph_reduces = self._grads_reduced        # the captured step contains its own all-reduces
+        self._grads_reduced = False
         self.optimizer.zero_grad()
         return self
+
+    def release_graph(self):
+        """Drop the captured step.  Must run before ``torch.distributed.destroy_process_group()`` when the graph
+        holds NCCL all-reduces: the communicator cannot be torn down while a graph still references it."""
+        g = getattr(self, "_graph", None)
+        self._graph = None
+        self._graph_reduces = False
+        if g is not None:
+            torch.cuda.synchronize()
+            g.reset()
+            del g
+            torch.cuda.synchronize()
 
     def _eager_step(self, batch):
         fused.begin_step()
         fused.advance_rng(self.device)           # in-graph increment: every replay draws new dropout masks
+        overlap = self._overlap_active()
+        if overlap:
+            fused.set_grad_boundary_callback(self._on_boundary)      # before forward: the boundaries are tape nodes
         eeg = self._regions(batch)
         ids = batch['decoder_input_ids'].to(self.device, non_blocking=True)
         labels = batch['labels'].to(self.device, non_blocking=True)
         out = self.forward_pass(eeg, ids, labels)
         if out.loss is None:
             raise RuntimeError("model returned no loss")
-        (out.loss / self.config['accumulation_steps']).backward()
+        if overlap:
+            self._works = []
+            try:
+                (out.loss / self.config['accumulation_steps']).backward()
+            finally:
+                fused.set_grad_boundary_callback(None)
+            self._reduce_runs(self._overlap_plan()['rest'])
+            for w in self._works:
+                w.wait()                         # the compute stream waits for the NCCL stream (no host sync)
+            self._works = []
+            self._grads_reduced = True
+        else:
+            (out.loss / self.config['accumulation_steps']).backward()
         return out.loss.detach()
 
     def train_step(self, batch):
@@ -180,6 +268,7 @@ class EEGTrainer:
             for k, dst in self._static.items():
                 dst.copy_(batch[k], non_blocking=True)
             self._graph.replay()
+            self._grads_reduced = self._graph_reduces
             return self._static_loss
         return self._eager_step(batch)
 

@@ -1,6 +1,7 @@
 """GPU tests of the train-step pieces: fused clip + AdamW against torch's own, and the
 EEGTrainer.train_epoch step semantics of the reference (trainer.py:69-151)."""
 import math
+import os
 
 import pytest
 import torch
@@ -208,3 +209,21 @@ def test_step_is_bit_reproducible():
     assert l1 == l2
     for n in g1:
         assert torch.equal(g1[n], g2[n]), n
+
+
+@pytest.mark.gpu
+def test_overlapped_allreduce_is_bitwise_equal_to_single_allreduce_two_gpus():
+    """Two ranks, identical replicas, per-rank batches: the gradients after the slice-wise all-reduce issued from
+    inside backward (eager and CUDA graph) equal the single post-backward all-reduce bit for bit
+    (tools/check_overlap.py).  Needs two GPUs; the single-GPU box of the round-end run skips it."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533",
+                          os.path.join(root, "tools", "check_overlap.py"), "--batch", "16"],
+                         capture_output=True, text=True, timeout=400)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "'all_ranks_ok': True" in res.stdout
