@@ -77,6 +77,127 @@ def apply_augmentation(reg: torch.Tensor, sigma: torch.Tensor, scale: torch.Tens
 
 
 # ------------------------------------------------------------------------------------------ dataset
+# ------------------------------------------------------------------------------------------ binary trial store
+class TrialStore:
+    """Flat binary store of the trials.
+
+    The reference unpickles a whole run file for every ``__getitem__`` (``dataset.py:153-170``, ~4 ms per sample,
+    LRU of 32 files).  The store is written once from the same pickles -- same order as ``sample_index``, malformed
+    entries kept as invalid slots so indices do not shift -- and then memory-mapped: an item is a (C, T) float32
+    slice, a batch is one gather into a pinned buffer followed by one H2D copy.
+
+    Layout: ``b"EEGXTS01"`` | u64 header length | JSON header {n, C, T, data_offset, valid[], texts[]} | padding to
+    4096 | float32 data (n, C, T), little endian, C-contiguous."""
+
+    MAGIC = b"EEGXTS01"
+
+    def __init__(self, path: str):
+        import json
+        with open(path, 'rb') as fh:
+            if fh.read(8) != self.MAGIC:
+                raise ValueError(f"{path}: not a trial store")
+            hlen = int(np.frombuffer(fh.read(8), dtype='<u8')[0])
+            hdr = json.loads(fh.read(hlen).decode('utf-8'))
+        self.path, self.n, self.C, self.T = path, hdr['n'], hdr['C'], hdr['T']
+        self.valid = np.asarray(hdr['valid'], dtype=bool)
+        self.texts = hdr['texts']
+        self.data = np.memmap(path, dtype='<f4', mode='r', offset=hdr['data_offset'], shape=(self.n, self.C, self.T))
+        self._offset, self._trial_bytes = hdr['data_offset'], 4 * self.C * self.T
+        self._fd = os.open(path, os.O_RDONLY)
+
+    def __del__(self):
+        fd = getattr(self, '_fd', None)
+        if fd is not None:
+            try:
+                os.close(fd)
+            except OSError:
+                pass
+            self._fd = None
+
+    @classmethod
+    def build(cls, samples, path: str, n_channels: int) -> "TrialStore":
+        """``samples``: iterable of the reference's sample dicts ({'input_features': (1, C, T), 'text': str}) or
+        None / malformed entries, in ``sample_index`` order."""
+        import json
+        arrs, valid, texts = [], [], []
+        shape = None
+        for smp in samples:
+            ok = isinstance(smp, dict) and 'input_features' in smp and 'text' in smp
+            arr = np.asarray(smp['input_features'], dtype=np.float32) if ok else None
+            ok = ok and arr.ndim >= 2 and arr.shape[1] == n_channels
+            if ok:
+                arr = arr.squeeze()
+                ok = arr.ndim == 2 and (shape is None or arr.shape == shape)
+            if ok:
+                shape = arr.shape
+            arrs.append(arr if ok else None)
+            valid.append(bool(ok))
+            texts.append(smp.get('text', '') if ok else '')
+        if shape is None:
+            raise ValueError("no valid trial to store")
+        hdr = {'n': len(arrs), 'C': int(shape[0]), 'T': int(shape[1]), 'valid': valid, 'texts': texts, 'data_offset': 0}
+        for _ in range(2):                                         # the offset is part of the header it depends on
+            raw = json.dumps(hdr, ensure_ascii=False).encode('utf-8')
+            hdr['data_offset'] = (16 + len(raw) + 64 + 4095) // 4096 * 4096
+        raw = json.dumps(hdr, ensure_ascii=False).encode('utf-8')
+        zero = np.zeros(shape, dtype='<f4')
+        with open(path, 'wb') as fh:
+            fh.write(cls.MAGIC)
+            fh.write(np.asarray([len(raw)], dtype='<u8').tobytes())
+            fh.write(raw)
+            fh.write(b'\0' * (hdr['data_offset'] - 16 - len(raw)))
+            for arr in arrs:
+                fh.write((zero if arr is None else np.ascontiguousarray(arr, dtype='<f4')).tobytes())
+        return cls(path)
+
+    def __len__(self):
+        return self.n
+
+    def trial(self, idx: int) -> Optional[np.ndarray]:
+        return np.asarray(self.data[idx]) if self.valid[idx] else None
+
+    RING = 3
+    THREADS = max(1, min(8, (os.cpu_count() or 2) // 2))
+
+    def batch(self, indices, pin: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """(B, C, T) float32 host tensor (pinned when CUDA is present): one gather, ready for one H2D copy.
+        Without ``out`` the result lives in a ring of RING reusable staging buffers per batch size (fresh host
+        allocations cost more in first-touch page faults than the copy itself): it stays valid until RING later
+        calls with the same batch size."""
+        idx = np.asarray(indices, dtype=np.int64)
+        if not self.valid[idx].all():
+            raise ValueError(f"trial(s) {idx[~self.valid[idx]].tolist()} are malformed")
+        pin = pin and torch.cuda.is_available()
+        if out is None:
+            ring = self.__dict__.setdefault('_ring', {})
+            slot = ring.setdefault((len(idx), pin), {'bufs': [], 'next': 0})
+            if len(slot['bufs']) < self.RING:
+                slot['bufs'].append(torch.empty((len(idx), self.C, self.T), dtype=torch.float32, pin_memory=pin))
+            out = slot['bufs'][slot['next'] % len(slot['bufs'])]
+            slot['next'] += 1
+        elif tuple(out.shape) != (len(idx), self.C, self.T) or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError("out must be a contiguous float32 (B, C, T) host tensor")
+        order = np.argsort(idx, kind='stable')                     # ascending file offsets
+        dst = out.numpy()
+
+        def read(js):                                              # positional reads straight into the batch buffer
+            for j in js:
+                got = os.preadv(self._fd, [memoryview(dst[j]).cast('B')],
+                                self._offset + int(idx[j]) * self._trial_bytes)
+                if got != self._trial_bytes:
+                    raise IOError(f"{self.path}: short read for trial {int(idx[j])}")
+
+        nthr = min(self.THREADS, max(1, len(idx) // 8))
+        if nthr <= 1:
+            read(order)
+        else:                                                      # preadv releases the GIL: the copies run in parallel
+            if getattr(self, '_pool', None) is None:
+                from concurrent.futures import ThreadPoolExecutor
+                self._pool = ThreadPoolExecutor(max_workers=self.THREADS)
+            list(self._pool.map(read, np.array_split(order, nthr)))
+        return out
+
+
 class EEGDataset(torch.utils.data.Dataset):
     """Same constructor as the reference (dataset.py:23-24).  ``ds[i]`` returns
     ``{'raw': (125, T) float32, 'decoder_input_ids', 'labels', 'attention_mask'}``; ``collate_raw`` stacks
@@ -85,7 +206,7 @@ class EEGDataset(torch.utils.data.Dataset):
     four ``(B, C_r, T)`` tensors the reference's ``ds[i]['eeg']`` holds (augmented if enabled)."""
 
     def __init__(self, data_dir, csv_path, tokenizer, max_length=64, eps=1e-6, max_samples=None,
-                 data_augmentation=True, precompute_stats=False, device="cuda"):
+                 data_augmentation=True, precompute_stats=False, device="cuda", trial_store: Optional[str] = None):
         import pandas as pd
         self.tokenizer = tokenizer
         self.max_length = max_length
@@ -111,6 +232,9 @@ class EEGDataset(torch.utils.data.Dataset):
         self.sample_index = self._build_sample_index()
         self._normalizer = None
         self._load_file = lru_cache(maxsize=32)(self._load_file_uncached)
+        self.store = TrialStore(trial_store) if trial_store else None
+        if self.store is not None and len(self.store) != len(self.sample_index):
+            raise ValueError(f"trial store holds {len(self.store)} trials, the pickles {len(self.sample_index)}")
 
     # -- indexing / loading (dataset.py:71-100, 153-170) ------------------------------------------------
     def _build_sample_index(self):
@@ -131,7 +255,18 @@ class EEGDataset(torch.utils.data.Dataset):
             loaded = pickle.load(fh)
         return loaded if isinstance(loaded, list) else [loaded]
 
+    def build_trial_store(self, path: str) -> TrialStore:
+        """Write the binary store from the pickles (once) and switch this dataset to it."""
+        def samples():
+            for info in self.sample_index:
+                yield self._load_file(info['file'])[info['index']]
+        self.store = TrialStore.build(samples(), path, len(self.ch_names))
+        return self.store
+
     def _raw(self, idx) -> Optional[dict]:
+        if self.store is not None:
+            arr = self.store.trial(idx)
+            return None if arr is None else {'eeg': arr, 'text': self.store.texts[idx]}
         info = self.sample_index[idx]
         sample = self._load_file(info['file'])[info['index']]
         if not isinstance(sample, dict) or 'input_features' not in sample or 'text' not in sample:
@@ -171,6 +306,23 @@ class EEGDataset(torch.utils.data.Dataset):
     @staticmethod
     def collate_raw(items):
         return {k: torch.stack([it[k] for it in items]) for k in items[0]}
+
+    def fetch(self, indices) -> dict:
+        """A whole batch by index list: with a trial store the raw trials are ONE gather into a pinned buffer
+        (no per-item tensors, no default_collate); tokens are computed once per sample and cached."""
+        if self.store is None:
+            return self.collate_raw([self[int(i)] for i in indices])
+        if not hasattr(self, '_tok_cache'):
+            self._tok_cache = {}
+        toks = []
+        for i in indices:
+            i = int(i)
+            if i not in self._tok_cache:
+                self._tok_cache[i] = self._safe_tokenize(self.store.texts[i])
+            toks.append(self._tok_cache[i])
+        out = {'raw': self.store.batch(indices)}
+        out.update({k: torch.stack([t[k] for t in toks]) for k in toks[0]})
+        return out
 
     # -- GPU normalisation / augmentation -----------------------------------------------------------------
     def normalizer(self) -> RegionNormalizer:

@@ -56,6 +56,48 @@ def test_dataset_mirror_index_and_tokens(ref, tokenizer):
     assert batch["raw"].shape == (2, 125, 64) and batch["labels"].shape == (2, 16)
 
 
+def _same_bits(a, b):
+    """Bit-pattern equality (the fixture trials contain NaN / inf on purpose)."""
+    if a.dtype.is_floating_point:
+        return a.shape == b.shape and torch.equal(a.contiguous().view(torch.int32), b.contiguous().view(torch.int32))
+    return torch.equal(a, b)
+
+
+def test_trial_store_serves_the_same_items_as_the_pickles(tokenizer, tmp_path):
+    """Binary trial store (row f2): built from the pickles, memory-mapped, item-for-item identical (bit-exact,
+    floats and token ids), malformed slots preserved, batches gathered in one go."""
+    import pickle
+    ds = _dataset(tokenizer, device="cpu")
+    path = str(tmp_path / "trials.eegx")
+    store = ds.build_trial_store(path)
+    assert len(store) == len(ds) and store.valid.all() and (store.C, store.T) == (125, 64)
+    plain = _dataset(tokenizer, device="cpu")
+    again = _dataset(tokenizer, device="cpu", trial_store=path)              # re-opened from disk
+    for i in range(len(ds)):
+        a, b = plain[i], again[i]
+        for k in a:
+            assert _same_bits(a[k], b[k]), (i, k)
+    idx = [5, 0, 3, 3]
+    got = again.fetch(idx)
+    want = plain.collate_raw([plain[i] for i in idx])
+    assert set(got) == set(want)
+    for k in want:
+        assert _same_bits(got[k], want[k]), k
+    assert _same_bits(plain.fetch(idx)["raw"], want["raw"])                  # fetch() without a store: same result
+    # malformed entries keep their slot (indices must not shift) and are refused like the pickle path refuses them
+    good = {"input_features": np.ones((1, 125, 8), np.float32), "text": "a"}
+    bad = {"input_features": np.ones((1, 7, 8), np.float32), "text": "b"}
+    st = pkg.TrialStore.build([good, bad, None, good], str(tmp_path / "m.eegx"), 125)
+    assert st.valid.tolist() == [True, False, False, True] and st.trial(1) is None
+    assert st.batch([3, 0], pin=False).shape == (2, 125, 8)
+    with pytest.raises(ValueError):
+        st.batch([0, 1], pin=False)
+    with pytest.raises(ValueError):
+        pkg.TrialStore(os.path.join(FIX, "vocab.txt"))                       # not a store
+    with pytest.raises(ValueError):
+        _dataset(tokenizer, device="cpu", trial_store=str(tmp_path / "m.eegx"))   # 4 trials vs the pickles' count
+
+
 def test_dataset_mirror_rejects_bad_input(tokenizer, tmp_path):
     with pytest.raises(FileNotFoundError):
         pkg.EEGDataset(str(tmp_path / "missing"), os.path.join(FIX, "montage.csv"), tokenizer)
