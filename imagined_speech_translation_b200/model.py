@@ -42,6 +42,7 @@ class BARTDecoder(nn.Module):
         self.autocast_dtype = autocast_dtype
         act = self.bart.config.activation_function
         self.fused_decoder = act == "gelu"          # our decoder path implements exact GELU only
+        self.native_generate = True                 # False: generate_from_eeg always calls transformers.generate
 
     def create_encoder_sequence(self, eeg_feat):
         B = eeg_feat.shape[0]
@@ -84,15 +85,27 @@ class BARTDecoder(nn.Module):
         on the tcgen05 GEMM and the fused kernels, the loss through the fused LM-head cross-entropy."""
         from transformers.modeling_outputs import Seq2SeqLMOutput
         bart = self.bart
-        dec = bart.model.decoder
         cfg = bart.config
-        tr = dec.training
         B, L = decoder_input_ids.shape
         d = cfg.d_model
         n_mem = cfg.encoder_layers
         proj = run_sequential(self.eeg_to_bart, eeg_feat.to(torch.bfloat16))                 # (B, d) bf16
         mem = proj.unsqueeze(1).expand(B, n_mem, d).reshape(B * n_mem, d)                    # repeated 6x (bart_decoder.py:29-33)
+        h = self._decoder_hidden(mem, decoder_input_ids, bart.model.decoder.training)
+        loss, logits = nn_ops.lm_head_cross_entropy(h, bart.lm_head.weight, bart.final_logits_bias.reshape(-1),
+                                                    labels.reshape(-1))
+        return Seq2SeqLMOutput(loss=loss, logits=logits.view(B, L, -1))
 
+    def _decoder_hidden(self, mem, decoder_input_ids, training):
+        """The decoder stack: token + position embeddings, LayerNorm, 6 post-LN layers.  mem: (B * n_mem, d) bf16,
+        decoder_input_ids: (B, L).  Returns the last hidden states (B * L, d) bf16."""
+        bart = self.bart
+        dec = bart.model.decoder
+        cfg = bart.config
+        tr = training
+        B, L = decoder_input_ids.shape
+        d = cfg.d_model
+        n_mem = mem.shape[0] // B
         emb = dec.embed_tokens(decoder_input_ids)                                            # includes embed_scale
         pos = dec.embed_positions.weight[dec.embed_positions.offset:dec.embed_positions.offset + L]
         h = (emb + pos.unsqueeze(0)).to(torch.bfloat16).reshape(B * L, d)
@@ -111,16 +124,20 @@ class BARTDecoder(nn.Module):
             f = nn_ops.linear(f, layer.fc2.weight, layer.fc2.bias)
             ln = layer.final_layer_norm
             h = fused.layer_norm(fused.add_dropout(h, f, p=p, training=tr), ln.weight, ln.bias, ln.eps)
-        loss, logits = nn_ops.lm_head_cross_entropy(h, bart.lm_head.weight, bart.final_logits_bias.reshape(-1),
-                                                    labels.reshape(-1))
-        return Seq2SeqLMOutput(loss=loss, logits=logits.view(B, L, -1))
+        return h
 
     def generate_from_eeg(self, eeg_feat, max_length=32, **kwargs):
         from transformers.modeling_outputs import BaseModelOutput
-        enc, mask = self.create_encoder_sequence(eeg_feat)
         cfg = dict(max_length=max_length, num_beams=3, early_stopping=True,
                    decoder_start_token_id=self.bart.config.decoder_start_token_id)
         cfg.update(kwargs)
+        from . import generation
+        if (self.fused_decoder and self.native_generate and eeg_feat.is_cuda and set(cfg) <= generation.SUPPORTED
+                and cfg['max_length'] <= fused.ATTN_MAX_S and cfg['num_beams'] >= 2):
+            # beam search on our kernels (generation.py); any other option set (and greedy decoding, which the
+            # library runs through a different routine) goes through transformers.generate
+            return generation.generate(self, eeg_feat, **cfg)
+        enc, mask = self.create_encoder_sequence(eeg_feat)
         return self.bart.generate(encoder_outputs=BaseModelOutput(last_hidden_state=enc.contiguous()),
                                   attention_mask=mask, **cfg)
 
