@@ -180,11 +180,31 @@ __device__ __forceinline__ void issue_tile_loads(const TunedArgs& a, float* xs, 
 // PK (ROWS == 1 only): the FIR runs on packed f32x2 values -- the row's two halves (t, t + 1024) move through
 // it as (lo, hi) pairs (FFMA2 with the taps as scalar-broadcast operands): half the FIR's issue slots.  The
 // pairs are interleaved into the STFT scratch region (free during the FIR) with the padded32 layout.
-template <int ROWS, int NT, bool PK>
+//
+// TC (ROWS == 1 only): the FIR runs on the tensor cores as a banded Toeplitz product, fp32-accurate through the
+// three-term TF32 split (x_hi h_hi + x_lo h_hi + x_hi h_lo).  One mma.sync.m16n8k8 tile is 128 consecutive
+// outputs, D[m][n] = y[t0 + 8m + n]; the contraction runs over the 72 inputs xs[t0 + 8m + u], u = 0..71 (9 k-tiles),
+// B[u][n] = taps_rev[u - n] (a constant band: the B fragments are split once per thread and live in registers),
+// A[m][u] = xs[t0 + 8m + u] -- the k-slots of a k-tile are permuted so that a thread's two A values of a row are
+// adjacent samples: 17 conflict-free LDS.64 feed all 27 MMAs of a tile.  The FFMA pipe, which bounds the scalar
+// FIR, is left to the STFT phase of the CTAs sharing the SM.
+__device__ __forceinline__ void split_tf32(float v, unsigned& hi, unsigned& lo) {
+    hi = (__float_as_uint(v) + 0x1000u) & 0xFFFFE000u;            // nearest 10-bit mantissa
+    lo = __float_as_uint(v - __uint_as_float(hi));                  // exact remainder (its low bits are dropped by the MMA)
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3,
+                                         unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int ROWS, int NT, bool PK, bool TC = false>
 __global__ void __launch_bounds__(NT, Cfg<ROWS, NT>::CTAS_PER_SM)
 dsp_tuned_kernel(const __grid_constant__ TunedArgs a) {
     static_assert(!PK || (ROWS == 1 && Cfg<ROWS, NT>::NGROUPS * 256 >= padded32(2 * (T / 2 + 64)) && NT >= 64),
                   "packed FIR: one row per tile, pairs must fit the STFT scratch");
+    static_assert(!TC || (ROWS == 1 && !PK), "tensor-core FIR: one row per tile");
     using C = Cfg<ROWS, NT>;
     constexpr int NWARPS = C::NWARPS;
     extern __shared__ __align__(128) float smem[];
@@ -216,6 +236,20 @@ dsp_tuned_kernel(const __grid_constant__ TunedArgs a) {
             spr[k] = __ldg(tb + 44 + 2 * k);
             spi[k] = __ldg(tb + 44 + 2 * k + 1);
         }
+    }
+
+    // tensor-core FIR: this thread's B fragments (the tap band), split into TF32 hi / lo once
+    const int mg = lane >> 2, mq = lane & 3;
+    unsigned bh[TC ? 9 : 1][2], bl[TC ? 9 : 1][2];
+    if constexpr (TC) {
+#pragma unroll
+        for (int kt = 0; kt < 9; ++kt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int d = 8 * kt + 2 * mq + e - mg;             // k-slot mq (+4) holds input offset 2 mq (+1)
+                const float tv = (d >= 0 && d <= 64) ? a.taps_rev[d] : 0.0f;
+                split_tf32(tv, bh[kt][e], bl[kt][e]);
+            }
     }
 
     // FIR zero halos (32 samples each side of every row), written once.
@@ -298,6 +332,52 @@ dsp_tuned_kernel(const __grid_constant__ TunedArgs a) {
                     }
                 }
             }
+        } else if constexpr (TC) {
+        // ------------------------------ FIR on the tensor cores ------------------------------
+        for (int blk = warp; blk < T / 128; blk += NWARPS) {
+            const int t0 = 128 * blk;
+            const float* src = xs + t0 + 8 * mg + 2 * mq;
+            unsigned ah[17][2], al[17][2];
+#pragma unroll
+            for (int j = 0; j < 17; ++j) {
+                const float2 v = *reinterpret_cast<const float2*>(src + 8 * j);
+                split_tf32(v.x, ah[j][0], al[j][0]);
+                split_tf32(v.y, ah[j][1], al[j][1]);
+            }
+            // six independent accumulator chains (3 terms x even / odd k-tiles): a single chain of 27 dependent
+            // MMAs is bound by the MMA latency, not by the tensor pipe
+            float c[6][4];
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) c[i][e] = 0.0f;
+#pragma unroll
+            for (int kt = 0; kt < 9; ++kt) {
+                const int par = kt & 1;
+                mma_tf32(c[0 + par], al[kt][0], al[kt + 8][0], al[kt][1], al[kt + 8][1], bh[kt][0], bh[kt][1]);
+                mma_tf32(c[2 + par], ah[kt][0], ah[kt + 8][0], ah[kt][1], ah[kt + 8][1], bl[kt][0], bl[kt][1]);
+                mma_tf32(c[4 + par], ah[kt][0], ah[kt + 8][0], ah[kt][1], ah[kt + 8][1], bh[kt][0], bh[kt][1]);
+            }
+            float acc[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)                            // small terms first
+                acc[e] = ((c[0][e] + c[1][e]) + (c[2][e] + c[3][e])) + (c[4][e] + c[5][e]);
+            float* yrow = ys;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {                           // rows mg and mg + 8 of the tile
+                const int t = t0 + 8 * (mg + 8 * h) + 2 * mq;
+                const float y0 = acc[2 * h], y1 = acc[2 * h + 1];
+                *reinterpret_cast<float2*>(yrow + 128 + t) = make_float2(y0, y1);
+                if (t <= 128) {                                     // reflect copy on the left: index -t for t in [1, 128]
+                    if (t >= 1) yrow[128 - t] = y0;
+                    if (t + 1 <= 128) yrow[128 - (t + 1)] = y1;
+                }
+                if (t + 1 >= T - 129) {                             // reflect copy on the right, t in [T-129, T-2]
+                    if (t >= T - 129 && t <= T - 2) yrow[2 * (T - 1) - t + 128] = y0;
+                    if (t + 1 <= T - 2) yrow[2 * (T - 1) - (t + 1) + 128] = y1;
+                }
+            }
+        }
         } else {
         // ------------------------------ FIR ------------------------------
         // lanes alternate rows; a thread owns outputs t = 8j .. 8j+7 of its row
@@ -523,15 +603,15 @@ bool dsp_tuned_supported(const eegx_dsp_plan* p) {
 int dsp_tuned_table_floats() { return 8 * LANE_TABLE; }
 void dsp_tuned_fill_tables(float* host) { fill_lane_tables(host); }
 
-template <int ROWS, int NT, bool PK = false>
+template <int ROWS, int NT, bool PK = false, bool TC = false>
 int launch_variant(const TunedArgs& a, cudaStream_t st) {
     using C = Cfg<ROWS, NT>;
-    EEGX_CUDA_CHECK(cudaFuncSetAttribute(dsp_tuned_kernel<ROWS, NT, PK>,
+    EEGX_CUDA_CHECK(cudaFuncSetAttribute(dsp_tuned_kernel<ROWS, NT, PK, TC>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
     const long long ntiles = (a.rows + ROWS - 1) / ROWS;
     const long long max_ctas = (long long)C::CTAS_PER_SM * kNumSMsB200;
     const int grid = (int)(ntiles < max_ctas ? ntiles : max_ctas);
-    dsp_tuned_kernel<ROWS, NT, PK><<<grid, NT, C::SMEM_BYTES, st>>>(a);
+    dsp_tuned_kernel<ROWS, NT, PK, TC><<<grid, NT, C::SMEM_BYTES, st>>>(a);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
 }
@@ -550,6 +630,8 @@ int launch_dsp_tuned(const eegx_dsp_plan* plan, const DspArgs& d, cudaStream_t s
     switch (plan->tuned_variant) {
         case 3: return launch_dsp_pair(plan, d, st);    // packed f32x2, 2 rows per tile (dsp_tuned2.cu)
         case 4: return launch_variant<1, 96, true>(a, st);   // 1 row per tile, packed half-row FIR
+        case 5: return launch_variant<1, 96, false, true>(a, st);    // 1 row per tile, FIR as 3xTF32 Toeplitz MMAs
+        case 6: return launch_variant<1, 128, false, true>(a, st);   // same, 4 warps (16 FIR blocks divide evenly)
         case 1: return launch_variant<1, 96>(a, st);    // 4 CTAs/SM x 3 warps, 1 row per tile
         case 2: return launch_variant<2, 192>(a, st);   // 2 CTAs/SM x 6 warps, 2 rows per tile
         default: return launch_variant<1, 96>(a, st);
