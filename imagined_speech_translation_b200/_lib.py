@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libeegx.so")
+LIB_PATH = os.environ.get("EEGX_LIB") or os.path.join(_PKG, "libeegx.so")     # EEGX_LIB: A/B builds of the same ABI
 
 _lib = None
 

@@ -37,9 +37,15 @@ bool pdl_enabled();
 }
 #ifdef __CUDACC__
 #include <utility>
+#ifdef EEGX_NO_GRIDDEP            // A/B build without the two instructions
+#define EEGX_PDL_SYNC()
+#define EEGX_PDL_TRIGGER()
+#define EEGX_PDL_WAIT()
+#else
 #define EEGX_PDL_SYNC() asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory")
 #define EEGX_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
 #define EEGX_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#endif
 namespace eegx {
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

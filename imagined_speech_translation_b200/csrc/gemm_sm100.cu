@@ -808,7 +808,9 @@ extern "C" int eegx_gemm_bf16(const eegx_gemm_desc* d, const void* A, const void
             const int bn = cand[i];
             if (bn == 64 && d->N > 64) continue;                       // 64 only for very narrow outputs
             if (bn > 64 && d->N <= 64) continue;
-            if (bn == 192) continue;                                   // measured slower than 256 (kept for force_block_n)
+            // 192: stand-alone it removes the half-empty last pass of the N = 768 encoder GEMMs (+3..5 % over 256), but
+            // inside the step, where four region streams share the SMs, it measured 0.3 ms slower: force_block_n only
+            if (bn == 192) continue;
             const bool pr = want_pair && bn >= 128;
             const double c = rounds_for(bn, pr) * (bn + 16) * eff[i];
             if (c < best) { best = c; block_n = bn; }
