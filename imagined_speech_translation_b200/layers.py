@@ -268,7 +268,10 @@ class Conv1DWithAttention(nn.Module):
         h = fused.grad_boundary(h, ('region', id(self)))        # attention stack + heads: gradients final here
 
         prev = None
+        mid = len(self.attn_layers) // 2
         for i, layer in enumerate(self.attn_layers):
+            if i == mid and i > 0:                              # layers mid.. and the heads: gradients final here
+                h = fused.grad_boundary(h, ('region_mid', id(self)))
             a = _mha(layer['attn'], _layer_norm(h, layer['attn_norm']), None, True)
             h = fused.add_dropout(h, a, p=self.dropout_light.p, training=self.training)
             saved = h

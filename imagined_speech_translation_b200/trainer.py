@@ -131,7 +131,7 @@ class EEGTrainer:
     def _overlap_plan(self):
         """Which slices of the flat gradient buffer are final at which point of backward (SURVEY.md 8(e):
         "bucketed and overlapped with backward").  Backward runs decoder -> fusion stage -> the four region
-        encoders (attention stack, then CNN); a `fused.grad_boundary` sits at each of those transitions and
+        encoders (attention stack -- split in two --, then CNN); a `fused.grad_boundary` sits at each of those transitions and
         its backward starts the all-reduce of the slice that has just become final.  Only what is left
         (region CNN stacks, tokens, positions: ~8 % of the bytes) is reduced after backward."""
         if self._plan is not None:
@@ -144,9 +144,17 @@ class EEGTrainer:
         for m in enc.region_encoders.values():
             if getattr(m, 'cnn_only', False):
                 continue
-            after = [p for sub in (m.attn_layers, m.cross_scale_attn, m.multi_scale_proj, m.projection,
-                                   m.diversity_head) for p in sub.parameters()]
-            plan[('region', id(m))] = opt.grad_runs(after)
+            # two points per region: halfway through the attention stack (upper layers + heads) and at its input
+            # (lower layers + cross_scale_attn, which every layer but the first uses)
+            mid = len(m.attn_layers) // 2
+            upper = [p for sub in (m.attn_layers[mid:], m.multi_scale_proj, m.projection, m.diversity_head)
+                     for p in sub.parameters()]
+            lower = [p for sub in (m.attn_layers[:mid], m.cross_scale_attn) for p in sub.parameters()]
+            if mid > 0:
+                plan[('region_mid', id(m))] = opt.grad_runs(upper)
+                plan[('region', id(m))] = opt.grad_runs(lower)
+            else:
+                plan[('region', id(m))] = opt.grad_runs(upper + lower)
         covered = sorted(r for runs in plan.values() for r in runs)
         rest, pos, total = [], 0, opt._all_grads.numel()
         for lo, hi in covered:
