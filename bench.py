@@ -362,6 +362,18 @@ def run_ours(args, rank, world, local_rank):
     value = B_PER_GPU * world / (ms_per_step / 1000.0)
     final_loss = float(loss)
 
+    if os.environ.get("EEGX_NCU_STEP") == "1":
+        # launch list of exactly one timed step for `ncu --profile-from-start off ...` (profiles/): the numbers of
+        # a run under the profiler are never reported, so stop here
+        torch.cuda.profiler.start()
+        step(batches[0])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        if world > 1:
+            from imagined_speech_translation_b200 import distributed as dp
+            dp.shutdown(trainer)
+        return
+
     # ---------------- end to end from pinned host batches ----------------
     gh = torch.Generator().manual_seed(99 + rank)
     host = []
@@ -471,7 +483,11 @@ def run_ours(args, rank, world, local_rank):
                          "method": "CUDA events around every GEMM launch of one single-stream eager step (GPU held "
                                    "behind the CPU so host work never falls between the events), empty-pair "
                                    "overhead calibrated and subtracted",
-                         "share_of_step": gemm_ms / ms_per_step},
+                         "share_of_step": gemm_ms / ms_per_step,
+                         "share_note": "GEMM kernel time / wall time of the step; the step packs ~41 ms of kernel time "
+                                       "(ncu launch list, profiles/r1_train_launch_shares.txt: GEMMs 44 % of it) into "
+                                       "~30 ms of wall time on 4 region streams, so the two shares differ by that factor "
+                                       "while the GEMM milliseconds agree"},
             "dsp": dsp,
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         }), flush=True)
