@@ -246,28 +246,32 @@ class EEGTrainer:
         fused.begin_step()
         fused.advance_rng(self.device)           # in-graph increment: every replay draws new dropout masks
         overlap = self._overlap_active()
-        if overlap:
-            fused.set_grad_boundary_callback(self._on_boundary)      # before forward: the boundaries are tape nodes
+        if not overlap:
+            out = self._forward_loss(batch)
+            (out.loss / self.config['accumulation_steps']).backward()
+            return out.loss.detach()
+        self._works = []
+        fused.set_grad_boundary_callback(self._on_boundary)          # before forward: the boundaries are tape nodes
+        try:
+            out = self._forward_loss(batch)
+            (out.loss / self.config['accumulation_steps']).backward()
+        finally:
+            fused.set_grad_boundary_callback(None)
+        self._reduce_runs(self._overlap_plan()['rest'])
+        for w in self._works:
+            w.wait()                             # the compute stream waits for the NCCL stream (no host sync)
+        self._works = []
+        self._grads_reduced = True
+        return out.loss.detach()
+
+    def _forward_loss(self, batch):
         eeg = self._regions(batch)
         ids = batch['decoder_input_ids'].to(self.device, non_blocking=True)
         labels = batch['labels'].to(self.device, non_blocking=True)
         out = self.forward_pass(eeg, ids, labels)
         if out.loss is None:
             raise RuntimeError("model returned no loss")
-        if overlap:
-            self._works = []
-            try:
-                (out.loss / self.config['accumulation_steps']).backward()
-            finally:
-                fused.set_grad_boundary_callback(None)
-            self._reduce_runs(self._overlap_plan()['rest'])
-            for w in self._works:
-                w.wait()                         # the compute stream waits for the NCCL stream (no host sync)
-            self._works = []
-            self._grads_reduced = True
-        else:
-            (out.loss / self.config['accumulation_steps']).backward()
-        return out.loss.detach()
+        return out
 
     def train_step(self, batch):
         """One micro-batch: preprocess (if raw) + forward + backward of loss / accumulation_steps.
