@@ -40,7 +40,7 @@ def beam_search(step_logits: Callable[[torch.Tensor], torch.Tensor], batch_size:
                 num_beams: int = 3, max_length: int = 16, min_length: int = 0, decoder_start_token_id: int,
                 eos_token_id: Optional[int], pad_token_id: Optional[int] = None,
                 forced_eos_token_id: Optional[int] = None, early_stopping=True, length_penalty: float = 1.0,
-                device="cuda") -> torch.Tensor:
+                device="cuda", select: Optional[Callable] = None) -> torch.Tensor:
     """Beam search as ``transformers`` 5.5 runs it for an encoder-decoder model whose prompt is the single
     ``decoder_start_token_id``.  ``step_logits(prefixes, parents)``: prefixes (batch*beams, cur_len) int64, parents
     (batch*beams,) int64 = for every row the row of the PREVIOUS call it continues (None on the first call; what a
@@ -52,7 +52,12 @@ def beam_search(step_logits: Callable[[torch.Tensor], torch.Tensor], batch_size:
     2 * beams continuations over all beams, retire those that ended (eos or max_length) into the finished set
     (score / generated_length ** length_penalty, best ``num_beams`` kept), continue with the best ``num_beams``
     unfinished ones; stop when every batch item has ``num_beams`` finished hypotheses (early_stopping=True), when
-    no running beam can beat the worst finished one, or when nothing can continue."""
+    no running beam can beat the worst finished one, or when nothing can continue.
+
+    ``select(logits, k, banned)`` -> (log-probabilities (rows, k) descending, token ids (rows, k)): optional fused
+    per-row log-softmax + top-k (``topk_logprobs``).  The best ``2 * beams`` continuations of a batch item are always
+    among the best ``2 * beams`` of each of its beams, so the V-wide log-softmax / add / top-k of the plain path
+    shrink to a top-k over ``beams * 2 * beams`` numbers."""
     if num_beams < 2:
         raise ValueError("beam_search needs num_beams >= 2 (the library decodes greedily through another routine)")
     dev = torch.device(device)
@@ -78,18 +83,32 @@ def beam_search(step_logits: Callable[[torch.Tensor], torch.Tensor], batch_size:
 
     while True:
         logits = step_logits(running[:, :, :cur].reshape(B * nb, cur), parents).to(torch.float32)
-        logp = torch.log_softmax(logits, dim=-1)
-        if eos_token_id is not None and cur < min_length:
-            logp[:, eos_token_id] = float("-inf")
-        if forced_eos_token_id is not None and cur == max_length - 1:
-            forced = torch.full_like(logp, float("-inf"))
-            forced[:, forced_eos_token_id] = 0
-            logp = forced
-        acc = (logp.view(B, nb, V) + run_score[:, :, None]).view(B, nb * V)
-        top_val, top_idx = torch.topk(acc, k=keep)
-        src_beam = top_idx // V
+        ban_eos = eos_token_id is not None and cur < min_length
+        force = forced_eos_token_id is not None and cur == max_length - 1
+        if select is None:
+            logp = torch.log_softmax(logits, dim=-1)
+            if ban_eos:
+                logp[:, eos_token_id] = float("-inf")
+            if force:
+                forced = torch.full_like(logp, float("-inf"))
+                forced[:, forced_eos_token_id] = 0
+                logp = forced
+            acc = (logp.view(B, nb, V) + run_score[:, :, None]).view(B, nb * V)
+            top_val, top_idx = torch.topk(acc, k=keep)
+            src_beam, tokens = top_idx // V, top_idx % V
+        else:
+            kk = min(keep, V)
+            if force:                                             # one continuation per beam, log-probability 0
+                row_val = torch.full((B * nb, kk), float("-inf"), device=dev)
+                row_val[:, 0] = 0
+                row_idx = torch.full((B * nb, kk), forced_eos_token_id, dtype=torch.int64, device=dev)
+            else:
+                row_val, row_idx = select(logits, kk, eos_token_id if ban_eos else -1)
+            acc = (row_val.view(B, nb, kk) + run_score[:, :, None]).view(B, nb * kk)
+            top_val, pos = torch.topk(acc, k=keep)
+            src_beam, tokens = pos // kk, torch.gather(row_idx.view(B, nb * kk), 1, pos)
         cand = _take(running, src_beam)
-        cand[:, :, cur] = top_idx % V
+        cand[:, :, cur] = tokens
         # which candidates just ended: eos as last token, or the length limit
         ended = torch.full((B, keep), cur + 1 >= max_length, dtype=torch.bool, device=dev)
         if eos_token_id is not None:
@@ -125,6 +144,20 @@ def beam_search(step_logits: Callable[[torch.Tensor], torch.Tensor], batch_size:
     out = finished[:, 0, :]
     out_len = prompt + int(fin_len[:, 0].max())
     return out[:, :out_len]
+
+
+def topk_logprobs(logits: torch.Tensor, k: int, banned: int = -1):
+    """Fused per-row log-softmax + top-k (``eegx_logsoftmax_topk_f32``): one read of the fp32 logits."""
+    from . import _lib
+    if not (logits.is_cuda and logits.dtype == torch.float32 and logits.dim() == 2 and logits.stride(1) == 1):
+        raise _lib.EegxError("topk_logprobs needs a CUDA float32 (rows, V) tensor with unit inner stride")
+    rows, V = logits.shape
+    val = torch.empty(rows, k, dtype=torch.float32, device=logits.device)
+    idx = torch.empty(rows, k, dtype=torch.int64, device=logits.device)
+    _lib.check(_lib.lib().eegx_logsoftmax_topk_f32(_lib.ptr(logits), logits.stride(0), rows, V, int(k), int(banned),
+                                                   _lib.ptr(val), _lib.ptr(idx), _lib.stream_ptr()),
+               "eegx_logsoftmax_topk_f32")
+    return val, idx
 
 
 # ---------------------------------------------------------------------------------------------- model side
@@ -307,4 +340,5 @@ def generate(bart_decoder, eeg_feat: torch.Tensor, **gen) -> torch.Tensor:
                        eos_token_id=eos, pad_token_id=gc.pad_token_id if gc.pad_token_id is not None else cfg.pad_token_id,
                        forced_eos_token_id=gc.forced_eos_token_id, early_stopping=gen.get("early_stopping", False),
                        length_penalty=float(gen.get("length_penalty", gc.length_penalty if gc.length_penalty is not None else 1.0)),
-                       device=eeg_feat.device)
+                       device=eeg_feat.device,
+                       select=topk_logprobs if getattr(bart_decoder, "fused_select", True) else None)

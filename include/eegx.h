@@ -341,6 +341,18 @@ int eegx_wake_dense_f64(double* w1, double* b1, double* w2, double* b2, const do
                         double* loss, double* probs, double* dx, void* workspace, size_t workspace_bytes,
                         void* stream);
 
+/* ------------------------------------------------------------------------
+ * Beam-search step: log-softmax + top-k of every logits row in one read (generation.py).
+ * Replaces the per-step log_softmax / add / torch.topk over (batch*beams, V) fp32 logits of transformers'
+ * GenerationMixin._beam_search (third-party; called from main_model/src/models/bart_decoder.py:59-79).
+ *   logits (rows, ld) fp32, V <= ld valid columns; k <= 16.
+ *   out_val[r, j] = logits[r, idx_j] - logsumexp(logits[r, :V]), j-th largest (ties: lower index first);
+ *   out_idx[r, j] = idx_j.  banned >= 0: token excluded from the selection, not from the log-sum-exp
+ *   (MinLengthLogitsProcessor semantics); pass -1 for none.
+ * ------------------------------------------------------------------------ */
+int eegx_logsoftmax_topk_f32(const float* logits, int64_t ld, int64_t rows, int64_t V, int32_t k, int64_t banned,
+                             float* out_val, int64_t* out_idx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,7 +22,15 @@ def _tiny_bart(seed, vocab=60, eos=5):
     return BartForConditionalGeneration(cfg).eval()
 
 
-def _library_and_ours(model, enc, **gen):
+def _torch_select(logits, k, banned):
+    """Reference for the fused per-row log-softmax + top-k."""
+    logp = torch.log_softmax(logits.float(), dim=-1)
+    if banned >= 0:
+        logp[:, banned] = float("-inf")
+    return torch.topk(logp, k=k, dim=-1)
+
+
+def _library_and_ours(model, enc, select=None, **gen):
     from transformers.modeling_outputs import BaseModelOutput
     B, n_mem, _ = enc.shape
     mask = torch.ones(B, n_mem)
@@ -44,7 +52,7 @@ def _library_and_ours(model, enc, **gen):
                                  pad_token_id=cfg.pad_token_id,
                                  forced_eos_token_id=model.generation_config.forced_eos_token_id,
                                  early_stopping=gen.get("early_stopping", False),
-                                 length_penalty=gen.get("length_penalty", 1.0), device="cpu")
+                                 length_penalty=gen.get("length_penalty", 1.0), device="cpu", select=select)
     return want, got
 
 
@@ -63,6 +71,18 @@ def test_beam_search_equals_transformers_generate(seed, gen):
     want, got = _library_and_ours(model, enc, **gen)
     assert want.shape == got.shape, (want.shape, got.shape)
     assert torch.equal(want, got)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_beam_search_with_per_row_selection_equals_transformers_generate(seed):
+    """The per-row top-2k shortcut (what the fused kernel feeds) selects exactly the library's continuations."""
+    model = _tiny_bart(seed)
+    torch.manual_seed(200 + seed)
+    enc = torch.randn(6, 6, 32)
+    for gen in (dict(num_beams=3, max_length=16, min_length=4, early_stopping=True),
+                dict(num_beams=4, max_length=12, min_length=2, early_stopping=False, length_penalty=2.0)):
+        want, got = _library_and_ours(model, enc, select=_torch_select, **gen)
+        assert want.shape == got.shape and torch.equal(want, got)
 
 
 def test_beam_search_early_finish_and_fill():
@@ -120,6 +140,29 @@ def test_step_logits_match_stock_forward():
         lp_g, lp_w = torch.log_softmax(got, -1), torch.log_softmax(want, -1)
         top = lp_w.topk(5, dim=-1).indices
         assert float((lp_g.gather(1, top) - lp_w.gather(1, top)).abs().max()) <= 0.15, L
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,V,k,banned", [(7, 51271, 6, 102), (3, 51271, 6, -1), (5, 1000, 16, 0), (4, 9, 8, 3),
+                                             (2, 300, 1, -1)])
+def test_fused_logsoftmax_topk_matches_torch(rows, V, k, banned):
+    torch.manual_seed(rows + V)
+    ld = (V + 7) // 8 * 8
+    buf = torch.randn(rows, ld, device="cuda") * 3
+    logits = buf[:, :V]
+    logits[0, : min(V, 5)] = 2.5                                   # exact ties: lower index first
+    val, idx = generation.topk_logprobs(logits, k, banned)
+    want_v, want_i = _torch_select(logits.clone(), k, banned)
+    assert float((val - want_v).abs().max()) <= 2e-5
+    ties = want_v[:, 1:] == want_v[:, :-1]
+    keep = torch.ones_like(want_i, dtype=torch.bool)
+    keep[:, 1:] &= ~ties
+    keep[:, :-1] &= ~ties
+    assert torch.equal(idx[keep], want_i[keep])
+    if banned >= 0:
+        assert not (idx == banned).any()
+    same = val[0, 1:] == val[0, :-1]                               # among equal values: ascending token ids
+    assert bool((idx[0, 1:][same] > idx[0, :-1][same]).all())
 
 
 @pytest.mark.gpu
