@@ -29,6 +29,7 @@ CONFIG = {
     'epochs': 100, 'batch_size': 4, 'accumulation_steps': 8, 'grad_clip_norm': 1.0,
     'brain_encoder_lr': 3e-4, 'bart_decoder_lr': 3e-5, 'projection_lr': 1e-4,
     'warmup_steps': 500, 'weight_decay': 0.01, 'log_interval': 20, 'seed': 42,
+    'generation': {'eval': {'max_length': 16, 'min_length': 4, 'num_beams': 3, 'early_stopping': True}},
     # DSP front-end keys (SURVEY.md section 5 "Config / flags")
     'fs': 256.0, 'band': (8.0, 30.0), 'numtaps': 65, 'n_fft': 256, 'hop': 64, 'log_eps': 1.0,
 }
@@ -283,6 +284,47 @@ class EEGTrainer:
             self._grads_reduced = self._graph_reduces
             return self._static_loss
         return self._eager_step(batch)
+
+    @torch.no_grad()
+    def evaluate(self, evaluator=None):
+        """``EEGTrainer.evaluate`` (trainer.py:153-212): validation loss and beam-search generation per batch,
+        decoded with the tokenizer.  Returns ``{'val_loss': ...}`` plus whatever ``evaluator.compute_all_metrics(
+        predictions, targets)`` adds (the reference's BLEU / ROUGE evaluator is host-side text processing and out of
+        scope; any object with that method can be passed).  The texts are kept in ``last_predictions`` /
+        ``last_targets``.  Unlike the reference, a failing batch raises instead of being skipped."""
+        was_training = self.model.training
+        self.model.eval()
+        gen_config = dict(self.config['generation']['eval'])
+        loss_sum = torch.zeros((), device=self.device, dtype=torch.float64)
+        n_samples = 0
+        predictions, targets = [], []
+        try:
+            for batch in self.val_loader:
+                eeg = self._regions(batch)
+                ids = batch['decoder_input_ids'].to(self.device, non_blocking=True)
+                labels = batch['labels'].to(self.device, non_blocking=True)
+                out = self.forward_pass(eeg, ids, labels)
+                if out.loss is not None:
+                    loss_sum += out.loss.double() * len(labels)
+                    n_samples += len(labels)
+                generated = self.model.generate(eeg_data=eeg, **gen_config).cpu()
+                labels_cpu = labels.cpu()
+                for i in range(len(generated)):
+                    if self.tokenizer is None:
+                        predictions.append(generated[i].tolist())
+                        targets.append(labels_cpu[i][labels_cpu[i] != -100].tolist())
+                        continue
+                    predictions.append(self.tokenizer.decode(generated[i], skip_special_tokens=True,
+                                                             clean_up_tokenization_spaces=True).strip())
+                    targets.append(self.tokenizer.decode(labels_cpu[i][labels_cpu[i] != -100], skip_special_tokens=True,
+                                                         clean_up_tokenization_spaces=True).strip())
+        finally:
+            self.model.train(was_training)
+        self.last_predictions, self.last_targets = predictions, targets
+        metrics = {'val_loss': float(loss_sum / n_samples) if n_samples else float('inf')}
+        if evaluator is not None:
+            metrics.update(evaluator.compute_all_metrics(predictions, targets))
+        return metrics
 
     def train_epoch(self, epoch):
         self.model.train()

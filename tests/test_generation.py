@@ -161,6 +161,11 @@ def test_fused_logsoftmax_topk_matches_torch(rows, V, k, banned):
     assert torch.equal(idx[keep], want_i[keep])
     if banned >= 0:
         assert not (idx == banned).any()
+    # a row start that is not 16-byte aligned takes the one-element-per-thread path: same answer
+    shifted = torch.empty(rows, ld + 8, device="cuda")[:, 1:1 + V]
+    shifted.copy_(logits)
+    val2, idx2 = generation.topk_logprobs(shifted, k, banned)
+    assert torch.equal(idx2, idx) and float((val2 - val).abs().max()) <= 2e-6
     same = val[0, 1:] == val[0, :-1]                               # among equal values: ascending token ids
     assert bool((idx[0, 1:][same] > idx[0, :-1][same]).all())
 

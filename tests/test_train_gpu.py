@@ -227,3 +227,41 @@ def test_overlapped_allreduce_is_bitwise_equal_to_single_allreduce_two_gpus():
                          capture_output=True, text=True, timeout=400)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "'all_ranks_ok': True" in res.stdout
+
+
+@pytest.mark.gpu
+def test_evaluate_reports_loss_and_generated_text():
+    """EEGTrainer.evaluate (trainer.py:153-212): eval-mode loss + beam-3 generation per validation batch, decoded
+    by the tokenizer; generation goes through generation.generate and equals model.generate on the same batch."""
+    from transformers import BertTokenizer
+    fix = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dataset")
+    tok = BertTokenizer(os.path.join(fix, "vocab.txt"), bos_token="[CLS]", eos_token="[SEP]")
+    torch.manual_seed(0)
+    counts = {"frontal": 16, "temporal": 16, "central": 16, "parietal": 16}
+    model = EEGDecodingModel(n_timepoints=33, region_channel_counts=counts).cuda()
+    tr.initialize_custom_weights(model)
+    g = torch.Generator().manual_seed(3)
+    batches = []
+    for _ in range(2):
+        labels = torch.randint(1, len(tok), (4, 16), generator=g)
+        labels[:, 12:] = -100
+        ids = torch.cat([torch.full((4, 1), 101), labels[:, :-1].clamp(min=0)], dim=1)
+        batches.append({"eeg": [torch.randn(4, 16, 33, generator=g) for _ in range(4)],
+                        "decoder_input_ids": ids, "labels": labels})
+    cfg = dict(tr.CONFIG, accumulation_steps=1)
+    trainer = tr.EEGTrainer(model, tok, None, batches, None, None, cfg)
+
+    class Count:
+        def compute_all_metrics(self, preds, targets):
+            return {"n": len(preds), "n_targets": len(targets)}
+
+    model.train()
+    metrics = trainer.evaluate(Count())
+    assert model.training                                           # mode restored
+    assert metrics["n"] == metrics["n_targets"] == 8 and math.isfinite(metrics["val_loss"])
+    assert all(isinstance(t, str) for t in trainer.last_predictions)
+    model.eval()
+    with torch.no_grad():
+        direct = model.generate(eeg_data=[r.cuda() for r in batches[0]["eeg"]], **cfg["generation"]["eval"]).cpu()
+    want = [tok.decode(direct[i], skip_special_tokens=True, clean_up_tokenization_spaces=True).strip() for i in range(4)]
+    assert trainer.last_predictions[:4] == want
