@@ -100,3 +100,50 @@ def test_optimizer_groups_route_by_name():
     groups = tr.get_optimizer_groups(M())
     assert [len(g['params']) for g in groups] == [2, 2, 2]
     assert [g['lr'] for g in groups] == [3e-4, 1e-4, 3e-5]
+
+
+def test_grad_boundary_fires_after_everything_downstream_has_its_gradient():
+    """The overlap of the all-reduce with backward rests on one property of `fused.grad_boundary`: when its backward
+    runs, every parameter used DOWNSTREAM of it (created later in forward) already holds its final gradient, while
+    parameters upstream do not yet.  Checked on CPU with plain modules, including a branch that re-joins (the
+    cross-scale pattern: a later layer also consumes an earlier activation directly)."""
+    from imagined_speech_translation_b200 import fused
+    torch.manual_seed(0)
+    up = torch.nn.Linear(8, 8)
+    mid = torch.nn.Linear(8, 8)
+    down1 = torch.nn.Linear(8, 8)
+    down2 = torch.nn.Linear(16, 4)
+    seen = {}
+
+    def cb(key):
+        seen[key] = {n: (m.weight.grad is not None) for n, m in
+                     dict(up=up, mid=mid, down1=down1, down2=down2).items()}
+
+    x = torch.randn(5, 8)
+    fused.set_grad_boundary_callback(cb)
+    try:
+        a = up(x)
+        early = a                                           # consumed again after the boundary, bypassing it
+        b = fused.grad_boundary(mid(torch.tanh(a)), 'B')
+        c = down1(torch.tanh(b))
+        out = down2(torch.cat([c, early], dim=1))
+        out.square().mean().backward()
+    finally:
+        fused.set_grad_boundary_callback(None)
+    assert seen['B'] == {'up': False, 'mid': False, 'down1': True, 'down2': True}
+    # without a callback the boundary is a no-op (same tensor object, nothing on the tape)
+    t = torch.randn(3, requires_grad=True)
+    assert fused.grad_boundary(t, 'x') is t
+
+
+def test_grad_runs_merge_adjacent_slices():
+    """FlatAdamW.grad_runs: contiguous runs of the flat gradient buffer for a parameter subset (offsets stubbed)."""
+    from imagined_speech_translation_b200.optim import FlatAdamW
+    ps = [torch.nn.Parameter(torch.zeros(n)) for n in (8, 16, 8, 24)]
+    opt = FlatAdamW.__new__(FlatAdamW)
+    opt._flat = [object()]
+    opt._offsets = {id(ps[0]): (0, 8), id(ps[1]): (8, 16), id(ps[2]): (24, 8), id(ps[3]): (32, 24)}
+    assert opt.grad_runs(ps) == [(0, 56)]
+    assert opt.grad_runs([ps[0], ps[2], ps[3]]) == [(0, 8), (24, 56)]
+    assert opt.grad_runs([ps[3], ps[1]]) == [(8, 24), (32, 56)]
+    assert opt.grad_runs([torch.nn.Parameter(torch.zeros(3))]) == []      # no gradient slot: skipped
