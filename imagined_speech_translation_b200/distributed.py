@@ -4,7 +4,7 @@ single collective the hot path needs.  Preprocessing needs none (every stage is 
 from __future__ import annotations
 
 import os
-from typing import Iterable, List, Optional, Sequence, Tuple
+from typing import Iterable, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist

@@ -13,7 +13,6 @@ Subclasses ``torch.optim.Optimizer`` so the reference's LR schedulers
 """
 from __future__ import annotations
 
-import ctypes as C
 from typing import Optional
 
 import torch

@@ -13,8 +13,6 @@ data parallelism the flat gradients are all-reduced once per optimizer step.
 from __future__ import annotations
 
 import math
-from typing import Optional
-
 import os
 
 import torch
