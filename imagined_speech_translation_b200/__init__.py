@@ -12,5 +12,5 @@ from .layers import Conv1DWithAttention, FeedForwardNetwork, SqueezeExciteBlock 
 from .brain_encoder import BrainRegionEncoder  # noqa: F401,E402
 from .optim import FlatAdamW  # noqa: F401,E402
 from .model import BARTDecoder, EEGDecodingModel  # noqa: F401,E402
-from .data import EEGDataset, TrialStore, apply_augmentation, augment_regions, build_region_indices  # noqa: F401,E402
+from .data import EEGDataset, PrefetchLoader, TrialStore, apply_augmentation, augment_regions, build_region_indices  # noqa: F401,E402
 from . import distributed, fused, ops  # noqa: F401,E402

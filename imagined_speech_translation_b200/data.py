@@ -338,3 +338,78 @@ class EEGDataset(torch.utils.data.Dataset):
     def to_regions(self, batch, generator: Optional[torch.Generator] = None) -> List[torch.Tensor]:
         regions = self.normalizer()(batch['raw'].to(self.device, non_blocking=True).float())
         return augment_regions(regions, generator=generator) if self.data_augmentation else regions
+
+
+# ------------------------------------------------------------------------------------------ batch prefetcher
+class PrefetchLoader:
+    """Iterates an ``EEGDataset`` in whole batches, built ``depth`` batches ahead by one background thread.
+
+    Stands where ``DataLoader(dataset, batch_size, shuffle, num_workers=0)`` stands in the reference
+    (``scripts/train.py:160-196``), but a batch is ONE ``dataset.fetch(indices)`` (with a trial store: one threaded
+    gather into a pinned staging buffer) instead of ``batch_size`` ``__getitem__`` calls + ``default_collate``, and the
+    next batches are assembled while the GPU runs the current step.  Order: a seeded permutation per epoch
+    (``set_epoch``), sequential without ``shuffle``.  ``depth`` must stay below ``TrialStore.RING`` so a staging
+    buffer is never rewritten while a yielded batch still points at it."""
+
+    def __init__(self, dataset, batch_size: int, shuffle: bool = True, drop_last: bool = False, seed: int = 0,
+                 depth: int = 2, indices: Optional[Sequence[int]] = None):
+        if batch_size < 1:
+            raise ValueError("batch_size must be >= 1")
+        if not 1 <= depth < TrialStore.RING:
+            raise ValueError(f"depth must be in [1, {TrialStore.RING - 1}]")
+        self.dataset, self.batch_size, self.shuffle, self.drop_last = dataset, int(batch_size), shuffle, drop_last
+        self.seed, self.depth, self.epoch = int(seed), int(depth), 0
+        self.indices = np.arange(len(dataset)) if indices is None else np.asarray(indices, dtype=np.int64)
+
+    def set_epoch(self, epoch: int) -> None:
+        self.epoch = int(epoch)
+
+    def __len__(self):
+        n = len(self.indices)
+        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+
+    def batches(self) -> List[np.ndarray]:
+        order = self.indices
+        if self.shuffle:
+            order = order[np.random.default_rng((self.seed, self.epoch)).permutation(len(order))]
+        out = [order[s:s + self.batch_size] for s in range(0, len(order), self.batch_size)]
+        if self.drop_last and out and len(out[-1]) < self.batch_size:
+            out.pop()
+        return out
+
+    def __iter__(self):
+        import queue
+        import threading
+        plan = self.batches()
+        q: "queue.Queue" = queue.Queue(maxsize=self.depth)
+        stop = threading.Event()
+
+        def work():
+            try:
+                for idx in plan:
+                    if stop.is_set():
+                        return
+                    item = self.dataset.fetch(idx)
+                    while not stop.is_set():
+                        try:
+                            q.put(item, timeout=0.1)
+                            break
+                        except queue.Full:
+                            continue
+                q.put(None)
+            except BaseException as exc:                              # surfaces in the consumer, never swallowed
+                q.put(exc)
+
+        t = threading.Thread(target=work, name="eegx-prefetch", daemon=True)
+        t.start()
+        try:
+            while True:
+                item = q.get()
+                if item is None:
+                    return
+                if isinstance(item, BaseException):
+                    raise item
+                yield item
+        finally:
+            stop.set()
+            t.join(timeout=5.0)
