@@ -24,6 +24,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+os.environ.setdefault("EEGX_BART_RANDOM_INIT", "1")   # synthetic benchmark: reference architecture, random weights (no HF cache here)
 import subprocess
 import sys
 import threading

@@ -307,9 +307,11 @@ class EEGDataset(torch.utils.data.Dataset):
     def collate_raw(items):
         return {k: torch.stack([it[k] for it in items]) for k in items[0]}
 
-    def fetch(self, indices) -> dict:
+    def fetch(self, indices, out: Optional[torch.Tensor] = None) -> dict:
         """A whole batch by index list: with a trial store the raw trials are ONE gather into a pinned buffer
-        (no per-item tensors, no default_collate); tokens are computed once per sample and cached."""
+        (no per-item tensors, no default_collate); tokens are computed once per sample and cached.  ``out``: the
+        caller's own (B, C, T) staging buffer (``PrefetchLoader`` passes the slot it has acquired); without it the
+        store's ring is used and the result is only valid until ``TrialStore.RING`` later calls."""
         if self.store is None:
             return self.collate_raw([self[int(i)] for i in indices])
         if not hasattr(self, '_tok_cache'):
@@ -320,9 +322,9 @@ class EEGDataset(torch.utils.data.Dataset):
             if i not in self._tok_cache:
                 self._tok_cache[i] = self._safe_tokenize(self.store.texts[i])
             toks.append(self._tok_cache[i])
-        out = {'raw': self.store.batch(indices)}
-        out.update({k: torch.stack([t[k] for t in toks]) for k in toks[0]})
-        return out
+        res = {'raw': self.store.batch(indices, out=out)}
+        res.update({k: torch.stack([t[k] for t in toks]) for k in toks[0]})
+        return res
 
     # -- GPU normalisation / augmentation -----------------------------------------------------------------
     def normalizer(self) -> RegionNormalizer:
@@ -348,18 +350,27 @@ class PrefetchLoader:
     (``scripts/train.py:160-196``), but a batch is ONE ``dataset.fetch(indices)`` (with a trial store: one threaded
     gather into a pinned staging buffer) instead of ``batch_size`` ``__getitem__`` calls + ``default_collate``, and the
     next batches are assembled while the GPU runs the current step.  Order: a seeded permutation per epoch
-    (``set_epoch``), sequential without ``shuffle``.  ``depth`` must stay below ``TrialStore.RING`` so a staging
-    buffer is never rewritten while a yielded batch still points at it."""
+    (``set_epoch``), sequential without ``shuffle``.
+
+    Staging-buffer lifetime (trial-store datasets).  The loader owns ``depth + keep + 2`` pinned buffers per batch
+    size: ``depth`` queued, one in the producer's hands, the one just yielded, and ``keep`` older ones.  A yielded
+    batch's ``'raw'`` tensor stays valid while the consumer works on it AND on the next ``keep`` batches; its slot
+    goes back to the producer when batch ``k + keep + 1`` is requested.  At that moment a CUDA event is recorded on
+    the consumer's current stream and the producer waits for it before overwriting the buffer, so an asynchronous
+    ``.to(device, non_blocking=True)`` (or a copy into the static inputs of a captured CUDA graph) that was
+    enqueued before the next batch was requested always reads the data it was given -- also when the host runs
+    several steps ahead of the GPU."""
 
     def __init__(self, dataset, batch_size: int, shuffle: bool = True, drop_last: bool = False, seed: int = 0,
-                 depth: int = 2, indices: Optional[Sequence[int]] = None):
+                 depth: int = 2, indices: Optional[Sequence[int]] = None, keep: int = 1):
         if batch_size < 1:
             raise ValueError("batch_size must be >= 1")
-        if not 1 <= depth < TrialStore.RING:
-            raise ValueError(f"depth must be in [1, {TrialStore.RING - 1}]")
+        if depth < 1 or keep < 0:
+            raise ValueError("depth must be >= 1 and keep >= 0")
         self.dataset, self.batch_size, self.shuffle, self.drop_last = dataset, int(batch_size), shuffle, drop_last
-        self.seed, self.depth, self.epoch = int(seed), int(depth), 0
+        self.seed, self.depth, self.keep, self.epoch = int(seed), int(depth), int(keep), 0
         self.indices = np.arange(len(dataset)) if indices is None else np.asarray(indices, dtype=np.int64)
+        self._slots: Dict[int, list] = {}          # batch size -> staging buffers owned by this loader
 
     def set_epoch(self, epoch: int) -> None:
         self.epoch = int(epoch)
@@ -377,22 +388,53 @@ class PrefetchLoader:
             out.pop()
         return out
 
+    def _staging(self, n: int) -> list:
+        store = getattr(self.dataset, 'store', None)
+        if store is None:
+            return []
+        bufs = self._slots.get(n)
+        if bufs is None:
+            pin = torch.cuda.is_available()
+            bufs = [torch.empty((n, store.C, store.T), dtype=torch.float32, pin_memory=pin)
+                    for _ in range(self.depth + self.keep + 2)]
+            self._slots[n] = bufs
+        return bufs
+
     def __iter__(self):
+        import collections
         import queue
         import threading
         plan = self.batches()
         q: "queue.Queue" = queue.Queue(maxsize=self.depth)
         stop = threading.Event()
+        use_slots = getattr(self.dataset, 'store', None) is not None
+        free: Dict[int, "queue.Queue"] = {}
+        if use_slots:
+            for n in sorted({len(b) for b in plan}):
+                free[n] = queue.Queue()
+                for buf in self._staging(n):
+                    free[n].put((buf, None))
 
         def work():
             try:
                 for idx in plan:
+                    buf = None
+                    if use_slots:
+                        while buf is None:                              # wait for a buffer the consumer has released
+                            if stop.is_set():
+                                return
+                            try:
+                                buf, event = free[len(idx)].get(timeout=0.1)
+                            except queue.Empty:
+                                continue
+                        if event is not None:
+                            event.synchronize()                        # copies the consumer enqueued from it are done
                     if stop.is_set():
                         return
-                    item = self.dataset.fetch(idx)
+                    item = self.dataset.fetch(idx, out=buf) if use_slots else self.dataset.fetch(idx)
                     while not stop.is_set():
                         try:
-                            q.put(item, timeout=0.1)
+                            q.put((item, buf), timeout=0.1)
                             break
                         except queue.Full:
                             continue
@@ -402,14 +444,26 @@ class PrefetchLoader:
 
         t = threading.Thread(target=work, name="eegx-prefetch", daemon=True)
         t.start()
+        held: "collections.deque" = collections.deque()
         try:
             while True:
-                item = q.get()
-                if item is None:
+                got = q.get()
+                if got is None:
                     return
-                if isinstance(item, BaseException):
-                    raise item
+                if isinstance(got, BaseException):
+                    raise got
+                item, buf = got
+                if buf is not None:
+                    held.append(buf)
                 yield item
+                # the consumer is asking for the next batch: the oldest held buffer goes back, fenced by an event
+                while len(held) > self.keep:
+                    old = held.popleft()
+                    event = None
+                    if torch.cuda.is_available() and torch.cuda.is_initialized():
+                        event = torch.cuda.Event()
+                        event.record()
+                    free[old.shape[0]].put((old, event))
         finally:
             stop.set()
             t.join(timeout=5.0)

@@ -86,16 +86,30 @@ def allreduce_gradients(params: Sequence[torch.nn.Parameter], group=None, averag
     return calls
 
 
+SHUTDOWN_STALLED_EXIT = 75      # EX_TEMPFAIL: teardown (graph release / barrier / destroy) did not finish in time
+
+
 def shutdown(trainer=None, grace_s: float = 30.0) -> None:
     """Orderly end of a data-parallel job: release captured graphs (they may hold NCCL kernels), barrier,
-    destroy the process group.  A watchdog ends the process with status 0 if the teardown itself stalls
-    (every result has been reported by then) instead of leaving the launcher waiting."""
+    destroy the process group.  If the teardown itself stalls for ``grace_s`` seconds -- a hung NCCL
+    communicator, or a peer rank that died and left the others at the barrier -- a watchdog says so on
+    stderr and ends the process with the NON-ZERO status ``SHUTDOWN_STALLED_EXIT``, so the launcher sees a
+    failure instead of waiting forever or recording a success."""
     import os
     import sys
     import threading
     sys.stdout.flush()
     sys.stderr.flush()
-    timer = threading.Timer(grace_s, lambda: os._exit(0))
+
+    def stalled():
+        try:
+            sys.stderr.write(f"eegx.distributed.shutdown: teardown stalled for {grace_s:.0f} s "
+                             f"(rank {os.environ.get('RANK', '0')}); exiting with status {SHUTDOWN_STALLED_EXIT}\n")
+            sys.stderr.flush()
+        finally:
+            os._exit(SHUTDOWN_STALLED_EXIT)
+
+    timer = threading.Timer(grace_s, stalled)
     timer.daemon = True
     timer.start()
     if trainer is not None:

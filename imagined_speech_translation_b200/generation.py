@@ -302,6 +302,35 @@ class GraphedDecoder:
 
 SUPPORTED = {"max_length", "min_length", "num_beams", "early_stopping", "decoder_start_token_id", "length_penalty"}
 
+# generation_config entries that switch on a logits processor / stopping criterion / decoding mode this path does
+# not implement, with the value that means "off" (transformers GenerationConfig defaults)
+_INACTIVE = {
+    "do_sample": (False, None), "num_beam_groups": (1, None), "diversity_penalty": (0.0, None), "penalty_alpha": (None,),
+    "repetition_penalty": (1.0, None), "encoder_repetition_penalty": (1.0, None),
+    "no_repeat_ngram_size": (0, None), "encoder_no_repeat_ngram_size": (0, None),
+    "bad_words_ids": (None,), "force_words_ids": (None,), "constraints": (None,), "sequence_bias": (None,),
+    "forced_bos_token_id": (None,), "suppress_tokens": (None,), "begin_suppress_tokens": (None,),
+    "forced_decoder_ids": (None,), "renormalize_logits": (False, None), "exponential_decay_length_penalty": (None,),
+    "remove_invalid_values": (False, None), "guidance_scale": (None, 1.0), "num_return_sequences": (1, None),
+    "max_new_tokens": (None,), "min_new_tokens": (None,), "stop_strings": (None,), "max_time": (None,),
+    "dola_layers": (None,), "watermarking_config": (None,), "token_healing": (False, None),
+    "output_scores": (False, None), "output_logits": (False, None, ), "return_dict_in_generate": (False, None),
+}
+
+
+def unsupported_generation_options(generation_config) -> list:
+    """Names of the options in a model's (checkpoint-inherited) ``generation_config`` that are active but not
+    implemented by ``beam_search`` -- ``transformers.generate`` applies them silently (e.g. ``no_repeat_ngram_size``
+    of a fine-tuned checkpoint), so the native path must not be taken when this list is non-empty."""
+    active = []
+    for name, off in _INACTIVE.items():
+        val = getattr(generation_config, name, None)
+        if isinstance(val, (list, tuple, dict)) and len(val) == 0:
+            continue
+        if not any(val is o or (o is not None and not isinstance(val, (list, tuple, dict)) and val == o) for o in off):
+            active.append(name)
+    return active
+
 
 @torch.no_grad()
 def generate(bart_decoder, eeg_feat: torch.Tensor, **gen) -> torch.Tensor:

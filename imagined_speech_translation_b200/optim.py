@@ -71,6 +71,12 @@ class FlatAdamW(torch.optim.Optimizer):
             flats.append(dict(p=flat_p, g=flat_g, m=torch.zeros_like(flat_p), v=torch.zeros_like(flat_p),
                               w16=flat_w16, params=ps))
         self._flat = flats
+        # parameters left outside (no gradient at build time) and the addresses the views must keep: step() checks both
+        self._outside = [p for g in self.param_groups for p in g['params'] if id(p) not in self._offsets]
+        self._expected_ptr = [(p, p.data_ptr(), p.grad.data_ptr()) for f in flats if f is not None for p in f['params']]
+        pending, self._pending_state = getattr(self, "_pending_state", None), None
+        if pending is not None:
+            self._import_state(pending)
         self._norm_sq = torch.zeros(1, device=dev)
         self._ws = torch.empty(_lib.lib().eegx_sumsq_workspace_bytes(), dtype=torch.uint8, device=dev)
 
@@ -107,6 +113,7 @@ class FlatAdamW(torch.optim.Optimizer):
             raise ValueError("closure is not supported")
         if self._flat is None:
             self._build()
+        self._check_bindings()
         lib = _lib.lib()
         st = _lib.stream_ptr()
         self._step += 1
@@ -134,6 +141,95 @@ class FlatAdamW(torch.optim.Optimizer):
                 p._eegx_w16_ver = p._version       # the shadow matches the parameter as of now
         nn_ops.clear_pack_cache()      # parameters changed behind autograd's back: derived packs are stale
         return None
+
+    def _check_bindings(self):
+        """The flat buffers are only correct while every parameter still IS its view of them: fail loudly when a
+        parameter got its first gradient after the buffers were laid out (it would never be updated nor clipped),
+        or when ``.data`` / ``.grad`` was rebound behind the optimizer's back (``model.to()``, ``load_state_dict``
+        with ``assign=True``, ``zero_grad(set_to_none=True)`` by foreign code)."""
+        for p in self._outside:
+            if p.grad is not None:
+                raise _lib.EegxError(
+                    "FlatAdamW: a parameter received its first gradient after the flat buffers were built "
+                    f"(shape {tuple(p.shape)}); run the first optimizer step on a batch that exercises every "
+                    "trainable parameter, or rebuild the optimizer")
+        for p, ptr, gptr in self._expected_ptr:
+            if p.data_ptr() != ptr or p.grad is None or p.grad.data_ptr() != gptr:
+                raise _lib.EegxError(
+                    f"FlatAdamW: parameter of shape {tuple(p.shape)} no longer points into the flat buffers "
+                    "(its .data or .grad was rebound after the first step); rebuild the optimizer")
+
+    # ------------------------------------------------------------------ checkpoint interchange
+    def state_dict(self):
+        """``torch.optim.AdamW``'s layout: ``state[i] = {'step', 'exp_avg', 'exp_avg_sq'}`` per parameter index in
+        ``param_groups`` order (parameters that never received a gradient have no entry, as in torch), so a
+        checkpoint written here resumes under ``torch.optim.AdamW`` and vice versa (reference
+        ``trainer.py:339-385`` stores ``optimizer.state_dict()`` under 'optimizer_state_dict')."""
+        base = super().state_dict()
+        if self._flat is None:
+            if getattr(self, "_pending_state", None) is not None:
+                base['state'] = self._pending_state
+            return base
+        index, i = {}, 0
+        for g in self.param_groups:
+            for p in g['params']:
+                index[id(p)] = i
+                i += 1
+        state = {}
+        for f in self._flat:
+            if f is None:
+                continue
+            lo = self._offsets[id(f['params'][0])][0]
+            for p in f['params']:
+                off = self._offsets[id(p)][0] - lo
+                k = p.numel()
+                state[index[id(p)]] = {
+                    'step': torch.tensor(float(self._step)),
+                    'exp_avg': f['m'][off:off + k].view_as(p).clone(),
+                    'exp_avg_sq': f['v'][off:off + k].view_as(p).clone(),
+                }
+        base['state'] = state
+        return base
+
+    def load_state_dict(self, state_dict):
+        groups = state_dict['param_groups']
+        if len(groups) != len(self.param_groups) or any(len(a['params']) != len(b['params'])
+                                                        for a, b in zip(groups, self.param_groups)):
+            raise ValueError("loaded state dict has different parameter groups")
+        for mine, theirs in zip(self.param_groups, groups):
+            mine.update({k: v for k, v in theirs.items() if k != 'params'})
+        state = {int(k): v for k, v in state_dict.get('state', {}).items()}
+        if self._flat is None:
+            self._pending_state = state            # applied when the flat buffers are laid out (first step)
+            steps = {int(float(v['step'])) for v in state.values()}
+            self._step = max(steps) if steps else 0
+            return
+        self._import_state(state)
+
+    def _import_state(self, state):
+        params = [p for g in self.param_groups for p in g['params']]
+        steps = set()
+        for f in self._flat:
+            if f is not None:
+                f['m'].zero_()
+                f['v'].zero_()
+        pos = {id(p): i for i, p in enumerate(params)}
+        for f in self._flat:
+            if f is None:
+                continue
+            lo = self._offsets[id(f['params'][0])][0]
+            for p in f['params']:
+                st = state.get(pos[id(p)])
+                if st is None:
+                    continue
+                off = self._offsets[id(p)][0] - lo
+                k = p.numel()
+                f['m'][off:off + k].copy_(st['exp_avg'].reshape(-1))
+                f['v'][off:off + k].copy_(st['exp_avg_sq'].reshape(-1))
+                steps.add(int(float(st['step'])))
+        if len(steps) > 1:
+            raise _lib.EegxError(f"FlatAdamW keeps one step counter; the loaded state has {sorted(steps)}")
+        self._step = steps.pop() if steps else 0
 
     def grad_norm(self) -> torch.Tensor:
         """||g||_2 of the last clipped step (device scalar, no sync)."""

@@ -8,6 +8,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+# no network / HF cache here: the BART decoder is the reference architecture with random weights (explicit opt-in)
+os.environ.setdefault("EEGX_BART_RANDOM_INIT", "1")
 
 
 def pytest_configure(config):

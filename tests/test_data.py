@@ -126,7 +126,28 @@ def test_prefetch_loader_batches_in_seeded_order(tokenizer, tmp_path):
     with pytest.raises(IndexError):
         list(bad)
     with pytest.raises(ValueError):
-        pkg.PrefetchLoader(ds, batch_size=2, depth=pkg.TrialStore.RING)
+        pkg.PrefetchLoader(ds, batch_size=2, depth=0)
+
+
+def test_prefetch_loader_never_rewrites_a_batch_the_consumer_still_holds(tokenizer, tmp_path):
+    """A slow consumer that keeps each yielded batch (uncloned) while the producer runs ahead: the batch it holds,
+    and the `keep` batches before it, must still hold their own trials when it finally reads them (round-1 bug:
+    depth + 2 live buffers against a ring of 3 -> batch k silently carried the trials of batch k + 3)."""
+    import time
+    ds = _dataset(tokenizer, device="cpu")
+    ds.build_trial_store(str(tmp_path / "t.eegx"))
+    for depth, keep in ((1, 1), (2, 1), (3, 0), (2, 3)):
+        loader = pkg.PrefetchLoader(ds, batch_size=2, shuffle=False, depth=depth, keep=keep)
+        plan = loader.batches()
+        window = []
+        for k, batch in enumerate(loader):
+            time.sleep(0.02)                                   # let the producer fill the queue and block
+            window.append((k, batch))
+            window = window[-(keep + 1):]
+            for j, old in window:                              # everything still inside the validity window
+                want = np.stack([ds.store.trial(int(i)) for i in plan[j]])
+                assert _same_bits(old["raw"], torch.from_numpy(want)), (depth, keep, k, j)
+        assert k == len(plan) - 1
 
 
 def test_dataset_mirror_rejects_bad_input(tokenizer, tmp_path):

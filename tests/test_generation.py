@@ -230,3 +230,49 @@ def test_generate_unsupported_options_use_the_library_path():
     feat = torch.randn(2, 768, device="cuda")
     out = dec.generate_from_eeg(feat, max_length=8, num_beams=2, no_repeat_ngram_size=2)     # not in generation.SUPPORTED
     assert out.shape[0] == 2 and out.shape[1] <= 8
+
+
+def test_checkpoint_generation_config_options_are_detected():
+    """Options a checkpoint's generation_config switches on (transformers.generate applies them silently) must be
+    reported, so generate_from_eeg leaves the native beam search for the library path."""
+    from transformers import GenerationConfig
+    assert generation.unsupported_generation_options(GenerationConfig()) == []
+    assert generation.unsupported_generation_options(_tiny_bart(0).generation_config) == []
+    for name, val in (("no_repeat_ngram_size", 3), ("repetition_penalty", 1.2), ("bad_words_ids", [[7]]),
+                      ("num_beam_groups", 2), ("do_sample", True), ("suppress_tokens", [4]), ("num_return_sequences", 2)):
+        gc = GenerationConfig()
+        setattr(gc, name, val)
+        assert generation.unsupported_generation_options(gc) == [name]
+
+
+@pytest.mark.gpu
+def test_generate_honours_the_checkpoints_generation_config():
+    """no_repeat_ngram_size set on bart.generation_config (not passed as a kwarg): the result must be the
+    library's, which never repeats a bigram -- the native path would."""
+    from transformers.modeling_outputs import BaseModelOutput
+    dec = _decoder(peaked=True)
+    feat = torch.randn(3, 768, device="cuda")
+    dec.bart.generation_config.no_repeat_ngram_size = 2
+    try:
+        out = dec.generate_from_eeg(feat, max_length=12, min_length=10, num_beams=2)
+        enc, mask = dec.create_encoder_sequence(feat)
+        want = dec.bart.generate(encoder_outputs=BaseModelOutput(last_hidden_state=enc.contiguous()), attention_mask=mask,
+                                 max_length=12, min_length=10, num_beams=2, early_stopping=True,
+                                 decoder_start_token_id=dec.bart.config.decoder_start_token_id)
+    finally:
+        dec.bart.generation_config.no_repeat_ngram_size = 0
+    assert torch.equal(out.cpu(), want.cpu())
+    for row in out.tolist():
+        grams = list(zip(row[1:], row[2:]))
+        body = [g for g in grams if g[0] != 0 and g[1] != 0]
+        assert len(body) == len(set(body))
+
+
+def test_load_bart_raises_without_a_checkpoint(monkeypatch):
+    """No silent random-weight fallback: a missing checkpoint is an error unless random init is requested."""
+    from imagined_speech_translation_b200.model import _load_bart
+    monkeypatch.setenv("EEGX_BART_RANDOM_INIT", "0")
+    monkeypatch.setenv("HF_HUB_OFFLINE", "1")
+    with pytest.raises(Exception):
+        _load_bart("fnlp/definitely-not-cached-bart")
+    assert _load_bart("random").config.vocab_size == 51271

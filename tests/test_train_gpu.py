@@ -43,6 +43,79 @@ def test_fused_clip_adamw_matches_torch():
     assert a[0].weight.grad is not None and float(a[0].weight.grad.abs().sum()) == 0.0
 
 
+def test_flat_adamw_state_dict_interchanges_with_torch_adamw():
+    """a checkpoint must carry the moments.  3 steps with ours -> state_dict -> torch.optim.AdamW
+    continues for 3 steps; the mirror run stays on torch.optim.AdamW throughout; then the other direction
+    (torch state -> FlatAdamW, before AND after its flat buffers exist)."""
+    groups = lambda m: [{'params': list(m[0].parameters()), 'lr': 3e-3},
+                        {'params': list(m[2].parameters()) + list(m[3].parameters()), 'lr': 1e-3}]
+    kw = dict(eps=1e-8, betas=(0.9, 0.999), weight_decay=0.01)
+
+    def run(m, opt, steps, seed, ours):
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        for _ in range(steps):
+            x = torch.randn(16, 37, device="cuda", generator=g)
+            m[2](m[1](m[0](x))).pow(2).sum().backward()
+            opt.step()
+            opt.zero_grad() if ours else opt.zero_grad(set_to_none=False)
+
+    a, b = _toy(5), _toy(5)
+    oa, ob = pkg.FlatAdamW(groups(a), **kw), torch.optim.AdamW(groups(b), **kw)
+    run(a, oa, 3, 11, True); run(b, ob, 3, 11, False)
+    sd = oa.state_dict()
+    assert set(sd['state']) == set(ob.state_dict()['state'])              # the unused layer has no entry in either
+    for k, st in ob.state_dict()['state'].items():
+        torch.testing.assert_close(sd['state'][k]['exp_avg'], st['exp_avg'], rtol=2e-6, atol=1e-9)
+        torch.testing.assert_close(sd['state'][k]['exp_avg_sq'], st['exp_avg_sq'], rtol=2e-6, atol=1e-12)
+        assert float(sd['state'][k]['step']) == float(st['step']) == 3.0
+    # ours -> torch
+    c = _toy(5)
+    c.load_state_dict(a.state_dict())
+    oc = torch.optim.AdamW(groups(c), **kw)
+    oc.load_state_dict(sd)
+    run(c, oc, 3, 12, False); run(b, ob, 3, 12, False)
+    for pc, pb in zip(c.parameters(), b.parameters()):
+        torch.testing.assert_close(pc, pb, rtol=5e-6, atol=5e-7)
+    # torch -> ours, loaded before the flat buffers exist (applied at the first step) ...
+    d = _toy(5)
+    d.load_state_dict(b.state_dict())
+    od = pkg.FlatAdamW(groups(d), **kw)
+    od.load_state_dict(ob.state_dict())
+    assert od.state_dict()['state'].keys() == ob.state_dict()['state'].keys()
+    # ... and after
+    e = _toy(5)
+    e.load_state_dict(b.state_dict())
+    oe = pkg.FlatAdamW(groups(e), **kw)
+    run(e, oe, 1, 99, True)
+    with torch.no_grad():
+        for pe, pb in zip(e.parameters(), b.parameters()):
+            pe.copy_(pb)                                                     # in place: the views stay bound
+    oe.load_state_dict(ob.state_dict())
+    run(d, od, 2, 13, True); run(e, oe, 2, 13, True); run(b, ob, 2, 13, False)
+    for pd, pe, pb in zip(d.parameters(), e.parameters(), b.parameters()):
+        torch.testing.assert_close(pd, pb, rtol=5e-6, atol=5e-7)
+        torch.testing.assert_close(pe, pb, rtol=5e-6, atol=5e-7)
+
+
+def test_flat_adamw_fails_loudly_when_a_parameter_escapes_the_flat_buffers():
+    m = _toy(2)
+    opt = pkg.FlatAdamW([{'params': list(m.parameters()), 'lr': 1e-3}])
+    x = torch.randn(4, 37, device="cuda")
+    m[2](m[1](m[0](x))).sum().backward()
+    opt.step(); opt.zero_grad()
+    m(x).sum().backward()                                   # the last layer gets its FIRST gradient only now
+    with pytest.raises(pkg.EegxError, match="first gradient"):
+        opt.step()
+    m2 = _toy(2)
+    opt2 = pkg.FlatAdamW([{'params': list(m2.parameters()), 'lr': 1e-3}])
+    m2(x).sum().backward()
+    opt2.step(); opt2.zero_grad()
+    m2[0].weight.data = m2[0].weight.data.clone()           # rebinding .data detaches the parameter from the buffers
+    m2(x).sum().backward()
+    with pytest.raises(pkg.EegxError, match="no longer points"):
+        opt2.step()
+
+
 def _batches(n, B, counts, T, seed):
     g = torch.Generator().manual_seed(seed)
     out = []

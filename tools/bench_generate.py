@@ -6,6 +6,7 @@ call through transformers.generate (fp32 and bf16 autocast) on the same GPU and 
 import argparse
 import json
 import os
+os.environ.setdefault("EEGX_BART_RANDOM_INIT", "1")   # synthetic benchmark: reference architecture, random weights (no HF cache here)
 import sys
 
 import torch

@@ -11,6 +11,7 @@ With more than two ranks the comparison is to 1e-6 relative (NCCL may pick diffe
 """
 import argparse
 import os
+os.environ.setdefault("EEGX_BART_RANDOM_INIT", "1")   # synthetic benchmark: reference architecture, random weights (no HF cache here)
 import sys
 
 import torch

@@ -1,4 +1,6 @@
 """Per-shape GEMM time inside one single-stream eager train step (CUDA events, GPU held behind the CPU)."""
+import os
+os.environ.setdefault("EEGX_BART_RANDOM_INIT", "1")   # synthetic benchmark: reference architecture, random weights (no HF cache here)
 import os, sys, collections
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

@@ -1,4 +1,6 @@
 """Profile one preprocess + train step at BASELINE config 3 (B per GPU from argv, default 256)."""
+import os
+os.environ.setdefault("EEGX_BART_RANDOM_INIT", "1")   # synthetic benchmark: reference architecture, random weights (no HF cache here)
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
