@@ -1,0 +1,145 @@
+"""Composed-model parity against goldens produced by the REFERENCE's own code (tests/golden/make_train_golden.py):
+
+* a12 -- ``initialize_custom_weights`` (scripts/train.py:108-126): which initialisation every parameter NAME
+  receives, compared name by name with what the reference function does to the reference model (CPU).
+* a9 / a10 -- ``EEGDecodingModel.forward`` + the reference ``EEGTrainer.train_epoch`` step: the loss of every
+  micro-batch, the pre-clip gradient norm of every learning-rate group at every optimizer step, and the weight
+  update of every parameter after 3 optimizer steps (2 micro-batches each, dropout 0, BatchNorm in train mode,
+  lr warm-up 0 -> lr/2 -> lr), at the STFT shape (B, 16*129, 33) and at configs[3]'s (B, 32*513, 17)   (GPU).
+
+Stated bounds, bf16 tensor-core path against the fp32 reference:
+  loss of every micro-batch            |delta| <= 3e-2   (losses range over 11.1 .. 11.7, i.e. the bound bites)
+  gradient norm per LR group           within 5 %
+  per-parameter gradient norm          within 10 %, median within 3 %  (parameters with a non-negligible gradient)
+  per-parameter update norm            within 10 %, median within 2 %
+  update direction (strided samples)   cosine >= 0.9
+"""
+import json
+import os
+import sys
+
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from param_recipe import (classify_init, fill_params, fill_sentinel, train_batches, zero_bart_dropout,  # noqa: E402
+                          zero_dropout)
+
+from imagined_speech_translation_b200 import trainer as tr  # noqa: E402
+from imagined_speech_translation_b200.model import EEGDecodingModel  # noqa: E402
+
+REGIONS = ["frontal", "temporal", "central", "parietal"]
+
+
+def test_initialize_custom_weights_routes_every_name_like_the_reference():
+    with open(os.path.join(HERE, "golden", "init_routing.json")) as fh:
+        want = json.load(fh)
+    torch.manual_seed(0)
+    model = EEGDecodingModel(n_timepoints=33, region_channel_counts={r: 16 for r in REGIONS}, hidden_dim=768)
+    names = {n for n, _ in model.named_parameters()}
+    assert names == set(want), (sorted(names - set(want))[:5], sorted(set(want) - names)[:5])   # same state_dict keys
+    fill_sentinel(model)
+    tr.initialize_custom_weights(model)
+    got = {n: classify_init(p) for n, p in model.named_parameters()}
+    wrong = {n: (got[n], want[n]) for n in want if got[n] != want[n]}
+    assert not wrong, list(wrong.items())[:5]
+    kinds = {v["kind"] for v in want.values()}
+    assert kinds == {"untouched", "ones", "zeros", "xavier_uniform_gain0.02", "normal_std0.02"}
+    # spot checks of the routing quirks SURVEY 8(a) row a12 lists
+    assert want["brain_encoder.region_encoders.frontal.cls_token"]["kind"] == "untouched"
+    assert want["brain_encoder.region_encoders.frontal.bn1.weight"]["kind"] == "untouched"          # 1-D, no 'norm'
+    assert want["brain_encoder.region_encoders.frontal.attn_layers.0.attn_norm.weight"]["kind"] == "ones"
+    assert want["brain_encoder.region_embeddings.weight"]["kind"] == "normal_std0.02"
+    assert want["bart_decoder.eeg_to_bart.0.weight"]["kind"] == "untouched"                          # 'bart' in the name
+    assert want["brain_encoder.region_encoders.frontal.conv1.weight"]["kind"] == "xavier_uniform_gain0.02"
+
+
+def _group_of(name):
+    return "brain_encoder" if "brain_encoder" in name else ("eeg_to_bart" if "eeg_to_bart" in name else "bart")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["stft", "long"])
+def test_three_optimizer_steps_match_the_reference_trainer(tag):
+    gold = torch.load(os.path.join(HERE, "golden", f"train_step_{tag}.pt"))
+    c = gold["cfg"]
+    counts = {r: c["channels"] for r in REGIONS}
+    torch.manual_seed(0)
+    model = EEGDecodingModel(n_timepoints=c["T"], region_channel_counts=counts, hidden_dim=768)
+    fill_params(model, seed=13)
+    zero_dropout(model)
+    zero_bart_dropout(model.bart_decoder.bart)
+    w0 = {n: p.detach().clone() for n, p in model.named_parameters()}
+    model = model.cuda()
+    cfg = dict(tr.CONFIG, accumulation_steps=c["accum"])
+    opt = tr.build_optimizer(model, cfg)
+    sched = tr.cosine_schedule_with_warmup(opt, c["warmup"], c["total"])
+    batches = train_batches(c["accum"] * c["opt_steps"], c["B"], counts, c["T"], seed=77)
+    trainer = tr.EEGTrainer(model, None, batches, batches, opt, sched, cfg)
+
+    losses, group_norms, param_norms, total_norms, lrs = [], [], [], [], []
+    real_step, real_opt = trainer.train_step, trainer._optimizer_step
+
+    def train_step(batch):
+        loss = real_step(batch)
+        losses.append(loss)
+        return loss
+
+    def optimizer_step(step_scheduler):
+        sq = {"brain_encoder": 0.0, "eeg_to_bart": 0.0, "bart": 0.0}
+        pn = {}
+        for n, p in model.named_parameters():
+            if p.grad is not None:
+                pn[n] = float(p.grad.double().norm())
+                sq[_group_of(n)] += pn[n] ** 2
+        group_norms.append({k: v ** 0.5 for k, v in sq.items()})
+        param_norms.append(pn)
+        lrs.append([g["lr"] for g in opt.param_groups])
+        real_opt(step_scheduler)
+        total_norms.append(float(opt.grad_norm()))
+
+    trainer.train_step, trainer._optimizer_step = train_step, optimizer_step
+    epoch_loss = trainer.train_epoch(0)
+    assert trainer.global_step == gold["global_step"] == c["opt_steps"]
+    assert lrs == gold["lr"]                                            # lr 0 on the first step, then warm-up
+
+    got_loss = [float(x) for x in losses]
+    for a, b in zip(got_loss, gold["loss"]):
+        assert abs(a - b) <= 3e-2, (got_loss, gold["loss"])
+    assert abs(epoch_loss - gold["epoch_loss"]) <= 3e-2
+
+    for step in range(c["opt_steps"]):
+        assert total_norms[step] == pytest.approx(gold["total_grad_norm"][step], rel=0.05)
+        for k, v in gold["group_grad_norm"][step].items():
+            assert group_norms[step][k] == pytest.approx(v, rel=0.05), (step, k)
+        ref = gold["param_grad_norm"][step]
+        floor = 1e-4 * max(ref.values())
+        ratios = torch.tensor([param_norms[step][n] / v for n, v in ref.items() if v > floor])
+        assert set(param_norms[step]) == set(ref)                       # the same parameters receive gradients
+        assert (ratios - 1).abs().median() <= 0.03 and (ratios - 1).abs().max() <= 0.10, \
+            (step, float((ratios - 1).abs().median()), float((ratios - 1).abs().max()))
+
+    # weights after the three steps: update norms of every parameter, directions on the sampled ones.  Parameters
+    # whose true gradient is zero (a bias in front of a train-mode BatchNorm) are driven by fp32 round-off in the
+    # reference (Adam normalises noise to +-lr) and are exactly still here: compared only where the gradient is real.
+    last = gold["param_grad_norm"][-1]
+    floor = 1e-4 * max(last.values())
+    live = [n for n, v in last.items() if v > floor and min(g[n] for g in gold["param_grad_norm"]) > floor]
+    now = dict(model.named_parameters())
+    ratios, cosines = [], {}
+    for n in live:
+        d = (now[n].detach().float().cpu() - w0[n]).flatten()
+        ratios.append(float(d.double().norm()) / gold["update_norm"][n])
+        if n in gold["update_sample"]:
+            stride = max(1, d.numel() // 4096)
+            mine = d[::stride][:4096].double()
+            ref_d = gold["update_sample"][n].double()
+            cosines[n] = float(torch.nn.functional.cosine_similarity(mine, ref_d, dim=0))
+    ratios = torch.tensor(ratios)
+    print(f"[{tag}] update-norm ratio median {float(ratios.median()):.4f} min {float(ratios.min()):.4f} "
+          f"max {float(ratios.max()):.4f}; cosines {{{', '.join(f'{k.split(chr(46), 2)[-1]}: {v:.3f}' for k, v in cosines.items())}}}")
+    assert (ratios - 1).abs().median() <= 0.02 and (ratios - 1).abs().max() <= 0.10
+    assert len(cosines) >= 12 and min(cosines.values()) >= 0.9, cosines
+    for n in gold["no_grad_params"]:
+        assert torch.equal(now[n].detach().cpu(), w0[n]), n            # BART encoder: never touched (no decay either)
