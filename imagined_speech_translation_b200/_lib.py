@@ -48,7 +48,9 @@ class GemmDesc(C.Structure):
                 ("stride_a", C.c_int64), ("stride_b", C.c_int64), ("stride_d", C.c_int64),
                 ("a_mn_major", C.c_int32), ("b_mn_major", C.c_int32), ("out_f32", C.c_int32),
                 ("epilogue", C.c_int32), ("accumulate", C.c_int32), ("force_block_n", C.c_int32),
-                ("alpha", C.c_float), ("reserved", C.c_int32)]
+                ("alpha", C.c_float), ("reserved", C.c_int32),
+                ("groups", C.c_int64), ("stride_a_g", C.c_int64), ("stride_b_g", C.c_int64),
+                ("stride_d_g", C.c_int64), ("stride_bias_g", C.c_int64)]
 
 
 SIGNATURES["eegx_gemm_bf16"] = (C.c_int, [C.POINTER(GemmDesc), C.c_void_p, C.c_void_p, C.c_void_p,
@@ -73,9 +75,11 @@ class AttnDesc(C.Structure):
 _P, _I64, _U32, _F, _I, _SZ = C.c_void_p, C.c_int64, C.c_uint32, C.c_float, C.c_int, C.c_size_t
 _RNG = [_P, _U32, _F]            # rng_state, site, p
 SIGNATURES.update({
-    "eegx_layernorm_fwd_bf16": (_I, [_P, _P, _P, _P, _P, _P, _I64, _I64, _F, _I] + _RNG + [_P]),
+    "eegx_layernorm_fwd_bf16": (_I, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _F, _I] + _RNG + [_P]),
     "eegx_layernorm_bwd_workspace_bytes": (_SZ, [_I64]),
-    "eegx_layernorm_bwd_bf16": (_I, [_P] * 9 + [_I, _P, _SZ, _I64, _I64, _I] + _RNG + [_P]),
+    "eegx_layernorm_bwd_bf16": (_I, [_P] * 9 + [_I, _P, _SZ, _I64, _I64, _I64, _I64, _I] + _RNG + [_P]),
+    "eegx_assemble_tokens_fwd_bf16": (_I, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I64, _I64, _I64, _P]),
+    "eegx_assemble_tokens_bwd_bf16": (_I, [_P, _P, _I64, _I64, _I64, _P]),
     "eegx_add_dropout_fwd_bf16": (_I, [_P, _P, _P, _I64, _F] + _RNG + [_P]),
     "eegx_dropout_scale_bf16": (_I, [_P, _P, _I64, _F] + _RNG + [_P]),
     "eegx_gelu_dropout_fwd_bf16": (_I, [_P, _P, _I64] + _RNG + [_P]),
@@ -83,14 +87,14 @@ SIGNATURES.update({
     "eegx_glu_fwd_bf16": (_I, [_P, _P, _I64, _I64] + _RNG + [_P]),
     "eegx_glu_bwd_bf16": (_I, [_P, _P, _P, _I64, _I64] + _RNG + [_P]),
     "eegx_colreduce_workspace_bytes": (_SZ, [_I64]),
-    "eegx_colsum_bf16": (_I, [_P, _I64, _I64, _I64, _P, _I, _P, _SZ, _P]),
-    "eegx_accumulate_partials_f32": (_I, [_P, _I64, _I64, _P, _I, _P]),
+    "eegx_colsum_bf16": (_I, [_P, _I64, _I64, _I64, _I64, _I64, _P, _I64, _I, _P, _SZ, _P]),
+    "eegx_accumulate_partials_f32": (_I, [_P, _I64, _I64, _I64, _P, _I64, _I, _P]),
     "eegx_accumulate_conv_wgrad_f32": (_I, [_P, _I64, _I64, _I64, _I64, _P, _I, _P]),
-    "eegx_bn_stats_bf16": (_I, [_P, _I64, _I64, _I64, _I64, _F, _P, _P, _P, _P, _F, _P, _SZ, _P]),
-    "eegx_bn_act_fwd_bf16": (_I, [_P] * 10 + [_I, _P, _I64, _I64, _I64, _I64] + _RNG + [_P]),
-    "eegx_bn_act_bwd_bf16": (_I, [_P] * 11 + [_I, _I, _P, _P, _P, _P, _SZ, _I64, _I64, _I64, _I64] + _RNG + [_P]),
-    "eegx_dwconv5_fwd_bf16": (_I, [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _P]),
-    "eegx_dwconv5_bwd_bf16": (_I, [_P, _P, _P, _P, _P, _P, _SZ, _I64, _I64, _I64, _I64, _P]),
+    "eegx_bn_stats_bf16": (_I, [_P, _I64, _I64, _I64, _I64, _I64, _F, _P, _P, _P, _P, _I64, _F, _P, _SZ, _P]),
+    "eegx_bn_act_fwd_bf16": (_I, [_P] * 10 + [_I, _P, _I64, _I64, _I64, _I64, _I64] + _RNG + [_P]),
+    "eegx_bn_act_bwd_bf16": (_I, [_P] * 11 + [_I, _I, _P, _P, _P, _P, _SZ, _I64, _I64, _I64, _I64, _I64] + _RNG + [_P]),
+    "eegx_dwconv5_fwd_bf16": (_I, [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _P]),
+    "eegx_dwconv5_bwd_bf16": (_I, [_P, _P, _P, _P, _P, _P, _SZ, _I64, _I64, _I64, _I64, _I64, _P]),
     "eegx_group_mean_bf16": (_I, [_P, _P, _I64, _I64, _I64, _I64, _P]),
     "eegx_group_mean_bwd_bf16": (_I, [_P, _P, _I64, _I64, _I64, _I64, _I, _P]),
     "eegx_se_scale_fwd_bf16": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64] + _RNG + [_P]),

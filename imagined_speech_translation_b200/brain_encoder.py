@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import fused, nn_ops
+from . import fused, grouped, nn_ops
 from .layers import Conv1DWithAttention, _layer_norm, _mha, run_sequential
 from .nn_ops import PAD
 
@@ -94,11 +94,42 @@ class BrainRegionEncoder(nn.Module):
         h = nn_ops.linear(h, layer.linear2.weight, layer.linear2.bias)
         return fused.add_dropout(x, h, p=layer.dropout2.p, training=tr)
 
+    def parameter_stacks(self):
+        """Lists of same-named, same-shaped parameters of the region encoders (one per region): laid out back to back
+        by ``FlatAdamW(stacks=...)`` they give the lock-step path (``grouped.py``) its stacked views."""
+        mods = [self.region_encoders[n] for n in self.region_names]
+        tables = [dict(m.named_parameters()) for m in mods]
+        out = []
+        for name, p in tables[0].items():
+            group = [t.get(name) for t in tables]
+            if all(q is not None and q.shape == p.shape for q in group):
+                out.append(group)
+        return out
+
+    def _lock_step(self, eeg_data):
+        """Can the regions run as ONE stacked pass (grouped.py)?  Needs the ParamStack views of FlatAdamW, equal
+        input shapes and a sequence the fused attention core serves."""
+        mods = [self.region_encoders[n] for n in self.region_names]
+        if not getattr(self, "lock_step_regions", True) or not grouped.available(mods):
+            return None
+        shp = eeg_data[0].shape
+        if any(x.shape != shp or not x.is_cuda for x in eeg_data) or shp[1] % 8 != 0:
+            return None
+        S = shp[2] + 4
+        for layer in list(mods[0].attn_layers) + [{'attn': mods[0].cross_scale_attn}]:
+            if not fused.attn_supported(S, S, self.hidden_dim // layer['attn'].num_heads):
+                return None
+        return mods
+
     def _region_features(self, eeg_data):
-        """The four region encoders are independent until the stack: run them on four streams
+        """Lock step when possible: every op of the four region encoders is one launch (grouped.py).  Otherwise
+        the four encoders are independent until the stack: run them on four streams
         (fork / join by events; also legal under CUDA-graph capture), so their many small kernels
         overlap instead of queueing behind each other (reference: sequential loop,
         brain_encoder.py:148-150)."""
+        mods = self._lock_step(eeg_data)
+        if mods is not None and grouped.MODE >= 2:
+            return grouped.forward(mods, list(eeg_data))
         if not getattr(self, "parallel_regions", True):
             return [self.region_encoders[n](eeg_data[i]) for i, n in enumerate(self.region_names)]
         cur = torch.cuda.current_stream()
@@ -114,16 +145,21 @@ class BrainRegionEncoder(nn.Module):
             s = self._streams[i % n_streams]
             with torch.cuda.stream(s):
                 eeg_data[i].record_stream(s)
-                f = self.region_encoders[name](eeg_data[i])
+                f = self.region_encoders[name]._cnn(eeg_data[i]) if mods is not None \
+                    else self.region_encoders[name](eeg_data[i])
             f.record_stream(cur)
             feats.append(f)
         for s in self._streams:
             cur.wait_event(s.record_event())
+        if mods is not None:        # grouped.MODE == 1: CNN stacks per region (above), attention stacks + heads in lock step
+            B, T = eeg_data[0].shape[0], eeg_data[0].shape[2]
+            return grouped.attention_and_heads(mods, torch.cat([f.reshape(B * T, -1) for f in feats], dim=0), B, T)
         return feats
 
     def forward(self, eeg_data):
         feats = self._region_features(eeg_data)
-        x = torch.stack(feats, dim=1)                            # (B, 4, d) fp32
+        # (B, 4, d) fp32
+        x = feats.transpose(0, 1).contiguous() if torch.is_tensor(feats) else torch.stack(feats, dim=1)
         x = fused.grad_boundary(x, ('fusion', id(self)))         # everything after the region encoders
         ms = self.apply_multi_scale_processing(x.to(torch.bfloat16))
         x = x + 0.3 * ms.float()

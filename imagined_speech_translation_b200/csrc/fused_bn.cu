@@ -20,8 +20,10 @@ namespace {
 using namespace eegx;
 
 struct RowGeom {
-    long long M;   // B * Tp
+    long long M;   // G * B * Tp: all rows of the guarded buffer
     int Tp, lo, hi;  // valid rows: lo <= (m mod Tp) < hi
+    long long Mg;  // rows per parameter group (B * Tp): rows [g*Mg, (g+1)*Mg) use parameter set g (the four
+    int G;         // region encoders run as ONE guarded buffer of G*B trials; G = 1: a single module)
     __device__ __forceinline__ bool valid(long long m) const {
         const int r = (int)(m % Tp);
         return r >= lo && r < hi;
@@ -39,9 +41,13 @@ __device__ __forceinline__ void col_reduce(const RowGeom& g, int C, float* __res
     constexpr int NW = CR_THREADS / 32;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int c = blockIdx.x * CR_COLS + 2 * lane;
-    const long long rows_per = (g.M + gridDim.y - 1) / gridDim.y;
-    const long long m0 = (long long)blockIdx.y * rows_per;
-    const long long m1 = m0 + rows_per < g.M ? m0 + rows_per : g.M;
+    // slabs never straddle a parameter group: gridDim.y = G * (slabs per group), group-major
+    const int spg = gridDim.y / g.G;
+    const int grp = blockIdx.y / spg;
+    const long long rows_per = (g.Mg + spg - 1) / spg;
+    const long long m0 = (long long)grp * g.Mg + (long long)(blockIdx.y - grp * spg) * rows_per;
+    const long long mend = (long long)(grp + 1) * g.Mg;
+    const long long m1 = m0 + rows_per < mend ? m0 + rows_per : mend;
     float acc[NACC][2];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k][0] = acc[k][1] = 0.0f;
@@ -53,7 +59,7 @@ __device__ __forceinline__ void col_reduce(const RowGeom& g, int C, float* __res
         const bool all_valid = g.lo == 0 && g.hi == g.Tp;
 #pragma unroll 4
         for (; m < m1; m += NW) {
-            if (all_valid || (r >= g.lo && r < g.hi)) f(m, c, acc);
+            if (all_valid || (r >= g.lo && r < g.hi)) f(m, c, grp, acc);
             r += step;
             if (r >= g.Tp) r -= g.Tp;
         }
@@ -83,7 +89,7 @@ __device__ __forceinline__ float2 ld2(const __nv_bfloat16* p) {
 __global__ void __launch_bounds__(CR_THREADS)
 bn_stats_partial_kernel(const __nv_bfloat16* __restrict__ y, RowGeom g, int C, float* __restrict__ part) {
     EEGX_PDL_SYNC();
-    col_reduce<2>(g, C, part, [&](long long m, int c, float (&acc)[2][2]) {
+    col_reduce<2>(g, C, part, [&](long long m, int c, int, float (&acc)[2][2]) {
         const float2 v = ld2(y + m * C + c);
         acc[0][0] += v.x; acc[0][1] += v.y;
         acc[1][0] = fmaf(v.x, v.x, acc[1][0]); acc[1][1] = fmaf(v.y, v.y, acc[1][1]);
@@ -92,10 +98,11 @@ bn_stats_partial_kernel(const __nv_bfloat16* __restrict__ y, RowGeom g, int C, f
 
 // plain column sums of a (rows, C) bf16 matrix (bias gradients): same skeleton, every row valid
 __global__ void __launch_bounds__(CR_THREADS)
-colsum_partial_kernel(const __nv_bfloat16* __restrict__ y, long long ld, RowGeom g, int C, float* __restrict__ part) {
+colsum_partial_kernel(const __nv_bfloat16* __restrict__ y, long long ld, long long y_gstride, RowGeom g, int C,
+                      float* __restrict__ part) {
     EEGX_PDL_SYNC();
-    col_reduce<1>(g, C, part, [&](long long m, int c, float (&acc)[1][2]) {
-        const float2 v = ld2(y + m * ld + c);
+    col_reduce<1>(g, C, part, [&](long long m, int c, int grp, float (&acc)[1][2]) {
+        const float2 v = ld2(y + grp * y_gstride + (m - grp * g.Mg) * ld + c);
         acc[0][0] += v.x; acc[0][1] += v.y;
     });
 }
@@ -105,10 +112,18 @@ colsum_partial_kernel(const __nv_bfloat16* __restrict__ y, long long ld, RowGeom
 __global__ void bn_stats_final_kernel(const float* __restrict__ part, int nslabs, int C, double n_valid, float eps,
                                       float* __restrict__ mean, float* __restrict__ rstd,
                                       float* __restrict__ running_mean, float* __restrict__ running_var,
-                                      float momentum) {
+                                      long long running_gstride, float momentum) {
     EEGX_PDL_SYNC();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
+    // blockIdx.y = parameter group: its nslabs partials, its (C) slice of every statistics vector
+    part += (long long)blockIdx.y * nslabs * 2 * C;
+    mean += (long long)blockIdx.y * C;
+    rstd += (long long)blockIdx.y * C;
+    if (running_mean != nullptr) {
+        running_mean += (long long)blockIdx.y * running_gstride;
+        running_var += (long long)blockIdx.y * running_gstride;
+    }
     double s = 0.0, q = 0.0;
     for (int b = 0; b < nslabs; ++b) {
         s += (double)part[((long long)b * 2 + 0) * C + c];
@@ -149,8 +164,9 @@ bn_act_fwd_kernel(BnSide a, BnSide r, int res_mode, __nv_bfloat16* __restrict__ 
         float o[8];
         if (m >= 0 && m < g.M && g.valid(m)) {
             float v[8], mu[8], rs[8], ga[8], be[8], msk[8];
+            const int po = (int)(m / g.Mg) * C;          // this row's parameter group
             load8(a.x + m * C + c, v);
-            load8f(a.mean + c, mu); load8f(a.rstd + c, rs); load8f(a.gamma + c, ga); load8f(a.beta + c, be);
+            load8f(a.mean + po + c, mu); load8f(a.rstd + po + c, rs); load8f(a.gamma + po + c, ga); load8f(a.beta + po + c, be);
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] = fmaf((v[e] - mu[e]) * rs[e], ga[e], be[e]);
             if (res_mode == 1) {
@@ -159,7 +175,7 @@ bn_act_fwd_kernel(BnSide a, BnSide r, int res_mode, __nv_bfloat16* __restrict__ 
                 for (int e = 0; e < 8; ++e) o[e] += v[e];
             } else if (res_mode == 2) {
                 load8(r.x + m * C + c, v);
-                load8f(r.mean + c, mu); load8f(r.rstd + c, rs); load8f(r.gamma + c, ga); load8f(r.beta + c, be);
+                load8f(r.mean + po + c, mu); load8f(r.rstd + po + c, rs); load8f(r.gamma + po + c, ga); load8f(r.beta + po + c, be);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) o[e] += fmaf((v[e] - mu[e]) * rs[e], ga[e], be[e]);
             }
@@ -176,23 +192,25 @@ bn_act_fwd_kernel(BnSide a, BnSide r, int res_mode, __nv_bfloat16* __restrict__ 
 
 // dpre = dout * dropout_mask * gelu'(pre), pre = bn(a) + residual; shared by the two backward passes
 __device__ __forceinline__ void bn_act_dpre(const BnSide& a, const BnSide& r, int res_mode,
-                                            const __nv_bfloat16* dout, long long m, int c, int C,
+                                            const __nv_bfloat16* dout, long long m, int c, int C, int po,
                                             const DropoutGen& gen, float (&dp)[2], float (&ha)[2], float (&hr)[2]) {
+    // po: offset of this row's parameter group in the (G, C) statistics / affine vectors
     const float2 va = ld2(a.x + m * C + c);
     const float2 d = ld2(dout + m * C + c);
-    ha[0] = (va.x - a.mean[c]) * a.rstd[c];
-    ha[1] = (va.y - a.mean[c + 1]) * a.rstd[c + 1];
-    float pre0 = fmaf(ha[0], a.gamma[c], a.beta[c]), pre1 = fmaf(ha[1], a.gamma[c + 1], a.beta[c + 1]);
+    const int pc = po + c;
+    ha[0] = (va.x - a.mean[pc]) * a.rstd[pc];
+    ha[1] = (va.y - a.mean[pc + 1]) * a.rstd[pc + 1];
+    float pre0 = fmaf(ha[0], a.gamma[pc], a.beta[pc]), pre1 = fmaf(ha[1], a.gamma[pc + 1], a.beta[pc + 1]);
     hr[0] = hr[1] = 0.0f;
     if (res_mode == 1) {
         const float2 vr = ld2(r.x + m * C + c);
         pre0 += vr.x; pre1 += vr.y;
     } else if (res_mode == 2) {
         const float2 vr = ld2(r.x + m * C + c);
-        hr[0] = (vr.x - r.mean[c]) * r.rstd[c];
-        hr[1] = (vr.y - r.mean[c + 1]) * r.rstd[c + 1];
-        pre0 += fmaf(hr[0], r.gamma[c], r.beta[c]);
-        pre1 += fmaf(hr[1], r.gamma[c + 1], r.beta[c + 1]);
+        hr[0] = (vr.x - r.mean[pc]) * r.rstd[pc];
+        hr[1] = (vr.y - r.mean[pc + 1]) * r.rstd[pc + 1];
+        pre0 += fmaf(hr[0], r.gamma[pc], r.beta[pc]);
+        pre1 += fmaf(hr[1], r.gamma[pc + 1], r.beta[pc + 1]);
     }
     float m0, m1;
     gen.mask_pair((unsigned long long)(m * C + c) >> 3, c & 7, m0, m1);
@@ -206,9 +224,9 @@ bn_act_bwd_reduce_kernel(BnSide a, BnSide r, int res_mode, const __nv_bfloat16* 
                          DropoutCfg dc, float* __restrict__ part) {
     EEGX_PDL_SYNC();
     const DropoutGen gen(dc);
-    col_reduce<3>(g, C, part, [&](long long m, int c, float (&acc)[3][2]) {
+    col_reduce<3>(g, C, part, [&](long long m, int c, int grp, float (&acc)[3][2]) {
         float dp[2], ha[2], hr[2];
-        bn_act_dpre(a, r, res_mode, dout, m, c, C, gen, dp, ha, hr);
+        bn_act_dpre(a, r, res_mode, dout, m, c, C, grp * C, gen, dp, ha, hr);
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             acc[0][e] += dp[e];
@@ -235,17 +253,19 @@ bn_act_bwd_apply_kernel(BnSide a, BnSide r, int res_mode, const __nv_bfloat16* _
         float oa[2] = {0.0f, 0.0f}, orr[2] = {0.0f, 0.0f};
         if (m >= 0 && m < g.M && g.valid(m)) {
             float dp[2], ha[2], hr[2];
-            bn_act_dpre(a, r, res_mode, dout, m, c, C, gen, dp, ha, hr);
+            const int grp = (int)(m / g.Mg), po = grp * C;
+            const float* sg = sums + (long long)grp * 3 * C;       // sums: (G, 3, C)
+            bn_act_dpre(a, r, res_mode, dout, m, c, C, po, gen, dp, ha, hr);
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const float s1 = train ? sums[c + e] * inv_n : 0.0f;
-                const float s2a = train ? sums[C + c + e] * inv_n : 0.0f;
-                oa[e] = a.gamma[c + e] * a.rstd[c + e] * (dp[e] - s1 - ha[e] * s2a);
+                const float s1 = train ? sg[c + e] * inv_n : 0.0f;
+                const float s2a = train ? sg[C + c + e] * inv_n : 0.0f;
+                oa[e] = a.gamma[po + c + e] * a.rstd[po + c + e] * (dp[e] - s1 - ha[e] * s2a);
                 if (res_mode == 1) {
                     orr[e] = dp[e];
                 } else if (res_mode == 2) {
-                    const float s2r = train ? sums[2 * C + c + e] * inv_n : 0.0f;
-                    orr[e] = r.gamma[c + e] * r.rstd[c + e] * (dp[e] - s1 - hr[e] * s2r);
+                    const float s2r = train ? sg[2 * C + c + e] * inv_n : 0.0f;
+                    orr[e] = r.gamma[po + c + e] * r.rstd[po + c + e] * (dp[e] - s1 - hr[e] * s2r);
                 }
             }
         }
@@ -259,11 +279,14 @@ bn_act_bwd_apply_kernel(BnSide a, BnSide r, int res_mode, const __nv_bfloat16* _
 // its 8 warps each sum every 8th slab (coalesced rows), then the warps are added in order.
 __global__ void __launch_bounds__(256)
 sum_partials_kernel(const float* __restrict__ part, int nslabs, int nacc, int C, float* __restrict__ out,
-                    int accumulate = 0) {
+                    long long out_gstride, int accumulate) {
     EEGX_PDL_SYNC();
     __shared__ float red[8][32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + lane, k = blockIdx.y;
+    // blockIdx.z = parameter group: its nslabs partials; its output block at out + z * out_gstride
+    part += (long long)blockIdx.z * nslabs * nacc * C;
+    out += (long long)blockIdx.z * out_gstride;
     float t = 0.0f;
     if (c < C)
         for (int b = wid; b < nslabs; b += 8) t += part[((long long)b * nacc + k) * C + c];
@@ -280,17 +303,21 @@ sum_partials_kernel(const float* __restrict__ part, int nslabs, int nacc, int C,
 
 // dst[i] (+)= sum_s part[s][i]  (split-K weight-gradient partials folded into the gradient buffer)
 __global__ void __launch_bounds__(256)
-accumulate_partials_kernel(const float* __restrict__ part, int s, long long n4, float* __restrict__ dst, int accumulate) {
+accumulate_partials_kernel(const float* __restrict__ part, int s, long long n4, long long per_group4,
+                           long long dst_gstride4, float* __restrict__ dst, int accumulate) {
+    // part: (s, n) contiguous with n = G * per_group; dst element (g, j) lives at g * dst_gstride + j
     EEGX_PDL_SYNC();
     const float4* p4 = reinterpret_cast<const float4*>(part);
     float4* d4 = reinterpret_cast<float4*>(dst);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        float4 a = accumulate ? d4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const long long grp = i / per_group4;
+        const long long di = grp * dst_gstride4 + (i - grp * per_group4);
+        float4 a = accumulate ? d4[di] : make_float4(0.f, 0.f, 0.f, 0.f);
         for (int k = 0; k < s; ++k) {
             const float4 v = __ldg(p4 + (long long)k * n4 + i);
             a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
         }
-        d4[i] = a;
+        d4[di] = a;
     }
 }
 
@@ -307,13 +334,14 @@ dwconv5_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
         const int c = (int)(i % c8) * 8;
         float o[8];
         if (m >= 0 && m < g.M && g.valid(m)) {
-            load8f(bias + c, o);
+            const int po = (int)(m / g.Mg) * C;          // parameter group: w (G, C, 5), bias (G, C)
+            load8f(bias + po + c, o);
 #pragma unroll
             for (int tap = 0; tap < 5; ++tap) {
                 float v[8];
                 load8(x + (m + tap - 2) * C + c, v);     // rows m-2..m+2 exist (pad >= 2) and are zero outside trials
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = fmaf(v[e], w[(c + e) * 5 + tap], o[e]);
+                for (int e = 0; e < 8; ++e) o[e] = fmaf(v[e], w[(po + c + e) * 5 + tap], o[e]);
             }
         } else {
 #pragma unroll
@@ -338,6 +366,7 @@ dwconv5_bwd_data_kernel(const __nv_bfloat16* __restrict__ dout, const float* __r
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = 0.0f;
         if (m >= 0 && m < g.M && g.valid(m)) {
+            const int po = (int)(m / g.Mg) * C;
 #pragma unroll
             for (int tap = 0; tap < 5; ++tap) {
                 const long long mm = m - tap + 2;
@@ -345,7 +374,7 @@ dwconv5_bwd_data_kernel(const __nv_bfloat16* __restrict__ dout, const float* __r
                     float v[8];
                     load8(dout + mm * C + c, v);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) o[e] = fmaf(v[e], w[(c + e) * 5 + tap], o[e]);
+                    for (int e = 0; e < 8; ++e) o[e] = fmaf(v[e], w[(po + c + e) * 5 + tap], o[e]);
                 }
             }
         }
@@ -358,7 +387,7 @@ __global__ void __launch_bounds__(CR_THREADS)
 dwconv5_bwd_weight_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ x, RowGeom g,
                           int C, float* __restrict__ part) {
     EEGX_PDL_SYNC();
-    col_reduce<6>(g, C, part, [&](long long m, int c, float (&acc)[6][2]) {
+    col_reduce<6>(g, C, part, [&](long long m, int c, int, float (&acc)[6][2]) {
         const float2 d = ld2(dout + m * C + c);
 #pragma unroll
         for (int tap = 0; tap < 5; ++tap) {
@@ -570,13 +599,14 @@ int ew_grid(long long n) {
     return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
-int slabs_for(long long M, int C) {
+// slabs PER GROUP (rows Mg each); G * slabs <= 64 (the workspace bound)
+int slabs_for(long long Mg, int C, int G = 1) {
     const int colblocks = (C + CR_COLS - 1) / CR_COLS;
-    long long s = (4LL * kNumSMsB200 + colblocks - 1) / colblocks;
-    const long long max_by_rows = (M + 31) / 32;
+    long long s = (4LL * kNumSMsB200 + (long long)colblocks * G - 1) / ((long long)colblocks * G);
+    const long long max_by_rows = (Mg + 31) / 32;
     if (s > max_by_rows) s = max_by_rows;
+    if (s > 64 / G) s = 64 / G;
     if (s < 1) s = 1;
-    if (s > 64) s = 64;
     return (int)s;
 }
 
@@ -584,9 +614,10 @@ int slabs_for(long long M, int C) {
 
 #define EEGX_GEOM_CHECK(name)                                                                                  \
     if (int rc = eegx::require_sm100()) return rc;                                                             \
-    EEGX_REQUIRE(B >= 0 && T >= 1 && pad >= 2 && C >= 8 && (C % 8) == 0, EEGX_ERR_SHAPE,                       \
-                 name ": need T >= 1, pad >= 2, C a multiple of 8");                                           \
-    const RowGeom g{(long long)B * (T + 2 * pad), (int)(T + 2 * pad), (int)pad, (int)(pad + T)};               \
+    EEGX_REQUIRE(B >= 0 && T >= 1 && pad >= 2 && C >= 8 && (C % 8) == 0 && G >= 1 && G <= 64, EEGX_ERR_SHAPE,   \
+                 name ": need T >= 1, pad >= 2, C a multiple of 8, 1 <= G <= 64");                             \
+    const RowGeom g{(long long)G * B * (T + 2 * pad), (int)(T + 2 * pad), (int)pad, (int)(pad + T),            \
+                    (long long)B * (T + 2 * pad), (int)G};                                                     \
     cudaStream_t st = static_cast<cudaStream_t>(stream);                                                       \
     (void)st
 
@@ -594,31 +625,33 @@ extern "C" {
 
 size_t eegx_colreduce_workspace_bytes(int64_t C) { return (size_t)64 * 6 * (size_t)C * sizeof(float); }
 
-int eegx_bn_stats_bf16(const void* y, int64_t B, int64_t T, int64_t pad, int64_t C, float eps, float* mean,
-                       float* rstd, float* running_mean, float* running_var, float momentum, void* workspace,
-                       size_t workspace_bytes, void* stream) {
+int eegx_bn_stats_bf16(const void* y, int64_t G, int64_t B, int64_t T, int64_t pad, int64_t C, float eps, float* mean,
+                       float* rstd, float* running_mean, float* running_var, int64_t running_gstride, float momentum,
+                       void* workspace, size_t workspace_bytes, void* stream) {
     EEGX_GEOM_CHECK("bn_stats");
     if (B == 0) return EEGX_OK;
     EEGX_REQUIRE(y && mean && rstd && workspace, EEGX_ERR_ARG, "bn_stats: NULL pointer");
     EEGX_REQUIRE(workspace_bytes >= eegx_colreduce_workspace_bytes(C), EEGX_ERR_WORKSPACE, "bn_stats: workspace too small");
-    const int slabs = slabs_for(g.M, (int)C);
+    const int slabs = slabs_for(g.Mg, (int)C, (int)G);
     float* part = static_cast<float*>(workspace);
-    dim3 grid((unsigned)((C + CR_COLS - 1) / CR_COLS), (unsigned)slabs);
+    dim3 grid((unsigned)((C + CR_COLS - 1) / CR_COLS), (unsigned)(slabs * G));
     eegx::launch(bn_stats_partial_kernel, grid, CR_THREADS, 0, st, static_cast<const __nv_bfloat16*>(y), g, (int)C, part);
-    eegx::launch(bn_stats_final_kernel, (int)((C + 127) / 128), 128, 0, st, part, slabs, (int)C, (double)B * (double)T, eps, mean,
-                                                                  rstd, running_mean, running_var, momentum);
+    eegx::launch(bn_stats_final_kernel, dim3((unsigned)((C + 127) / 128), (unsigned)G), 128, 0, st, part, slabs, (int)C,
+                 (double)B * (double)T, eps, mean, rstd, running_mean, running_var, (long long)running_gstride, momentum);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
 }
 
-int eegx_accumulate_partials_f32(const float* part, int64_t s, int64_t n, float* dst, int accumulate, void* stream) {
+int eegx_accumulate_partials_f32(const float* part, int64_t s, int64_t G, int64_t n, float* dst, int64_t dst_gstride,
+                                 int accumulate, void* stream) {
     if (int rc = eegx::require_sm100()) return rc;
-    EEGX_REQUIRE(s >= 1 && n >= 0 && (n % 4) == 0, EEGX_ERR_SHAPE, "accumulate_partials: n must be a multiple of 4");
+    EEGX_REQUIRE(s >= 1 && G >= 1 && n >= 0 && (n % 4) == 0 && (dst_gstride % 4) == 0, EEGX_ERR_SHAPE,
+                 "accumulate_partials: n and the group stride must be multiples of 4");
     if (n == 0) return EEGX_OK;
     EEGX_REQUIRE(part && dst, EEGX_ERR_ARG, "accumulate_partials: NULL pointer");
     EEGX_REQUIRE(eegx::aligned16(part) && eegx::aligned16(dst), EEGX_ERR_ALIGN, "accumulate_partials: 16-byte alignment");
-    eegx::launch(accumulate_partials_kernel, ew_grid(n / 4), 256, 0, static_cast<cudaStream_t>(stream), part, (int)s, n / 4, dst,
-                                                                                              accumulate);
+    eegx::launch(accumulate_partials_kernel, ew_grid(G * n / 4), 256, 0, static_cast<cudaStream_t>(stream), part, (int)s,
+                 (long long)(G * n / 4), (long long)(n / 4), (long long)((G > 1 ? dst_gstride : n) / 4), dst, accumulate);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
 }
@@ -637,27 +670,29 @@ int eegx_accumulate_conv_wgrad_f32(const float* part, int64_t s, int64_t Cout, i
     return EEGX_OK;
 }
 
-int eegx_colsum_bf16(const void* y, int64_t ld, int64_t rows, int64_t C, float* out, int accumulate, void* workspace,
-                     size_t workspace_bytes, void* stream) {
+int eegx_colsum_bf16(const void* y, int64_t ld, int64_t G, int64_t y_gstride, int64_t rows, int64_t C, float* out,
+                     int64_t out_gstride, int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
     if (int rc = eegx::require_sm100()) return rc;
-    EEGX_REQUIRE(rows >= 0 && C >= 2 && (C % 2) == 0 && ld >= C && (ld % 2) == 0, EEGX_ERR_SHAPE,
-                 "colsum: C and ld must be even, ld >= C");
+    EEGX_REQUIRE(rows >= 0 && C >= 2 && (C % 2) == 0 && ld >= C && (ld % 2) == 0 && G >= 1 && G <= 64 &&
+                     (y_gstride % 2) == 0, EEGX_ERR_SHAPE, "colsum: C, ld and the group stride must be even, ld >= C, 1 <= G <= 64");
     EEGX_REQUIRE(y && out && workspace, EEGX_ERR_ARG, "colsum: NULL pointer");
     EEGX_REQUIRE(workspace_bytes >= eegx_colreduce_workspace_bytes(C), EEGX_ERR_WORKSPACE, "colsum: workspace too small");
-    const RowGeom g{(long long)rows, 1, 0, 1};
+    const RowGeom g{(long long)rows * G, 1, 0, 1, (long long)rows, (int)G};     // rows per group, every row valid
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int slabs = slabs_for(g.M, (int)C);
+    const int slabs = slabs_for(g.Mg, (int)C, (int)G);
     float* part = static_cast<float*>(workspace);
-    dim3 grid((unsigned)((C + CR_COLS - 1) / CR_COLS), (unsigned)slabs);
-    eegx::launch(colsum_partial_kernel, grid, CR_THREADS, 0, st, static_cast<const __nv_bfloat16*>(y), ld, g, (int)C, part);
-    eegx::launch(sum_partials_kernel, dim3((unsigned)((C + 31) / 32), 1), 256, 0, st, part, slabs, 1, (int)C, out, accumulate);
+    dim3 grid((unsigned)((C + CR_COLS - 1) / CR_COLS), (unsigned)(slabs * G));
+    eegx::launch(colsum_partial_kernel, grid, CR_THREADS, 0, st, static_cast<const __nv_bfloat16*>(y), (long long)ld,
+                 (long long)y_gstride, g, (int)C, part);
+    eegx::launch(sum_partials_kernel, dim3((unsigned)((C + 31) / 32), 1, (unsigned)G), 256, 0, st, part, slabs, 1, (int)C, out,
+                 (long long)out_gstride, accumulate);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
 }
 
 int eegx_bn_act_fwd_bf16(const void* ya, const float* mean_a, const float* rstd_a, const float* gamma_a,
                          const float* beta_a, const void* yr, const float* mean_r, const float* rstd_r,
-                         const float* gamma_r, const float* beta_r, int res_mode, void* out, int64_t B, int64_t T,
+                         const float* gamma_r, const float* beta_r, int res_mode, void* out, int64_t G, int64_t B, int64_t T,
                          int64_t pad, int64_t C, const uint64_t* rng_state, uint32_t site, float p, void* stream) {
     EEGX_GEOM_CHECK("bn_act_fwd");
     if (B == 0) return EEGX_OK;
@@ -674,12 +709,12 @@ int eegx_bn_act_fwd_bf16(const void* ya, const float* mean_a, const float* rstd_
     return EEGX_OK;
 }
 
-/* sums: (3, C) fp32 out: [0] dbeta (both sides), [1] dgamma_a, [2] dgamma_r.  da / dr: guarded buffers
+/* sums: (G, 3, C) fp32 out: [0] dbeta (both sides), [1] dgamma_a, [2] dgamma_r.  da / dr: guarded buffers
  * (pointer to row m = 0), every row written. */
 int eegx_bn_act_bwd_bf16(const void* dout, const void* ya, const float* mean_a, const float* rstd_a,
                          const float* gamma_a, const float* beta_a, const void* yr, const float* mean_r,
                          const float* rstd_r, const float* gamma_r, const float* beta_r, int res_mode, int train,
-                         void* da, void* dr, float* sums, void* workspace, size_t workspace_bytes, int64_t B,
+                         void* da, void* dr, float* sums, void* workspace, size_t workspace_bytes, int64_t G, int64_t B,
                          int64_t T, int64_t pad, int64_t C, const uint64_t* rng_state, uint32_t site, float p,
                          void* stream) {
     EEGX_GEOM_CHECK("bn_act_bwd");
@@ -691,12 +726,13 @@ int eegx_bn_act_bwd_bf16(const void* dout, const void* ya, const float* mean_a, 
     const BnSide a{static_cast<const __nv_bfloat16*>(ya), mean_a, rstd_a, gamma_a, beta_a};
     const BnSide r{static_cast<const __nv_bfloat16*>(yr), mean_r, rstd_r, gamma_r, beta_r};
     const DropoutCfg dc{reinterpret_cast<const unsigned long long*>(rng_state), site, p};
-    const int slabs = slabs_for(g.M, (int)C);
+    const int slabs = slabs_for(g.Mg, (int)C, (int)G);
     float* part = static_cast<float*>(workspace);
-    dim3 grid((unsigned)((C + CR_COLS - 1) / CR_COLS), (unsigned)slabs);
+    dim3 grid((unsigned)((C + CR_COLS - 1) / CR_COLS), (unsigned)(slabs * G));
     eegx::launch(bn_act_bwd_reduce_kernel, grid, CR_THREADS, 0, st, a, r, res_mode, static_cast<const __nv_bfloat16*>(dout), g,
                                                           (int)C, dc, part);
-    eegx::launch(sum_partials_kernel, dim3((unsigned)((C + 31) / 32), 3), 256, 0, st, part, slabs, 3, (int)C, sums, 0);
+    eegx::launch(sum_partials_kernel, dim3((unsigned)((C + 31) / 32), 3, (unsigned)G), 256, 0, st, part, slabs, 3, (int)C, sums,
+                 (long long)(3 * C), 0);
     eegx::launch(bn_act_bwd_apply_kernel, ew_grid((g.M + 2 * pad) * (C / 2)), 256, 0, st, 
         a, r, res_mode, static_cast<const __nv_bfloat16*>(dout), sums, 1.0f / (float)((double)B * (double)T), train,
         static_cast<__nv_bfloat16*>(da), static_cast<__nv_bfloat16*>(dr), g, (int)pad, (int)C, dc);
@@ -704,7 +740,7 @@ int eegx_bn_act_bwd_bf16(const void* dout, const void* ya, const float* mean_a, 
     return EEGX_OK;
 }
 
-int eegx_dwconv5_fwd_bf16(const void* x, const float* w, const float* bias, void* out, int64_t B, int64_t T,
+int eegx_dwconv5_fwd_bf16(const void* x, const float* w, const float* bias, void* out, int64_t G, int64_t B, int64_t T,
                           int64_t pad, int64_t C, void* stream) {
     EEGX_GEOM_CHECK("dwconv5_fwd");
     if (B == 0) return EEGX_OK;
@@ -715,9 +751,9 @@ int eegx_dwconv5_fwd_bf16(const void* x, const float* w, const float* bias, void
     return EEGX_OK;
 }
 
-/* dw: (C, 5) fp32, db: (C) fp32.  dwdb_scratch: (6, C) fp32. */
+/* dw: (G, C, 5) fp32, db: (G, C) fp32.  dwdb_scratch: (G, 6, C) fp32. */
 int eegx_dwconv5_bwd_bf16(const void* dout, const void* x, const float* w, void* dx, float* dwdb_scratch,
-                          void* workspace, size_t workspace_bytes, int64_t B, int64_t T, int64_t pad, int64_t C,
+                          void* workspace, size_t workspace_bytes, int64_t G, int64_t B, int64_t T, int64_t pad, int64_t C,
                           void* stream) {
     EEGX_GEOM_CHECK("dwconv5_bwd");
     if (B == 0) return EEGX_OK;
@@ -725,17 +761,19 @@ int eegx_dwconv5_bwd_bf16(const void* dout, const void* x, const float* w, void*
     EEGX_REQUIRE(workspace_bytes >= eegx_colreduce_workspace_bytes(C), EEGX_ERR_WORKSPACE, "dwconv5_bwd: workspace too small");
     eegx::launch(dwconv5_bwd_data_kernel, ew_grid((g.M + 2 * pad) * (C / 8)), 256, 0, st, 
         static_cast<const __nv_bfloat16*>(dout), w, static_cast<__nv_bfloat16*>(dx), g, (int)pad, (int)C);
-    const int slabs = slabs_for(g.M, (int)C);
+    const int slabs = slabs_for(g.Mg, (int)C, (int)G);
     float* part = static_cast<float*>(workspace);
-    dim3 grid((unsigned)((C + CR_COLS - 1) / CR_COLS), (unsigned)slabs);
+    dim3 grid((unsigned)((C + CR_COLS - 1) / CR_COLS), (unsigned)(slabs * G));
     eegx::launch(dwconv5_bwd_weight_kernel, grid, CR_THREADS, 0, st, static_cast<const __nv_bfloat16*>(dout),
                                                            static_cast<const __nv_bfloat16*>(x), g, (int)C, part);
-    eegx::launch(sum_partials_kernel, dim3((unsigned)((C + 31) / 32), 6), 256, 0, st, part, slabs, 6, (int)C, dwdb_scratch, 0);
+    eegx::launch(sum_partials_kernel, dim3((unsigned)((C + 31) / 32), 6, (unsigned)G), 256, 0, st, part, slabs, 6, (int)C,
+                 dwdb_scratch, (long long)(6 * C), 0);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
 }
 
 int eegx_group_mean_bf16(const void* x, float* s, int64_t B, int64_t T, int64_t pad, int64_t C, void* stream) {
+    const int64_t G = 1;                  // per-trial kernel: the caller passes all G * B trials as B
     EEGX_GEOM_CHECK("group_mean");
     if (B == 0) return EEGX_OK;
     EEGX_REQUIRE(x && s, EEGX_ERR_ARG, "group_mean: NULL pointer");
@@ -747,6 +785,7 @@ int eegx_group_mean_bf16(const void* x, float* s, int64_t B, int64_t T, int64_t 
 
 int eegx_group_mean_bwd_bf16(const float* ds, void* dx, int64_t B, int64_t T, int64_t pad, int64_t C,
                              int accumulate, void* stream) {
+    const int64_t G = 1;                  // per-trial kernel: the caller passes all G * B trials as B
     EEGX_GEOM_CHECK("group_mean_bwd");
     if (B == 0) return EEGX_OK;
     EEGX_REQUIRE(ds && dx, EEGX_ERR_ARG, "group_mean_bwd: NULL pointer");
@@ -758,6 +797,7 @@ int eegx_group_mean_bwd_bf16(const float* ds, void* dx, int64_t B, int64_t T, in
 
 int eegx_se_scale_fwd_bf16(const void* x, const float* e, void* out, int64_t B, int64_t T, int64_t pad, int64_t C,
                            const uint64_t* rng_state, uint32_t site, float p, void* stream) {
+    const int64_t G = 1;                  // per-trial kernel: the caller passes all G * B trials as B
     EEGX_GEOM_CHECK("se_scale_fwd");
     if (B == 0) return EEGX_OK;
     EEGX_REQUIRE(x && e && out, EEGX_ERR_ARG, "se_scale_fwd: NULL pointer");
@@ -773,6 +813,7 @@ int eegx_se_scale_fwd_bf16(const void* x, const float* e, void* out, int64_t B, 
 int eegx_se_scale_bwd_bf16(const void* dout, const void* x, const float* e, void* dx, float* de, int64_t B,
                            int64_t T, int64_t pad, int64_t C, const uint64_t* rng_state, uint32_t site, float p,
                            void* stream) {
+    const int64_t G = 1;                  // per-trial kernel: the caller passes all G * B trials as B
     EEGX_GEOM_CHECK("se_scale_bwd");
     if (B == 0) return EEGX_OK;
     EEGX_REQUIRE(dout && x && e && dx && de, EEGX_ERR_ARG, "se_scale_bwd: NULL pointer");
@@ -791,6 +832,7 @@ int eegx_se_scale_bwd_bf16(const void* dout, const void* x, const float* e, void
  * the guarded buffer is written (zeros outside the valid rows). */
 int eegx_nct_to_rows_bf16(const float* x, int64_t x_bstride, void* out, int64_t B, int64_t T, int64_t pad,
                           int64_t C, void* stream) {
+    const int64_t G = 1;                  // per-trial kernel: the caller passes all G * B trials as B
     EEGX_GEOM_CHECK("nct_to_rows");
     if (B == 0) return EEGX_OK;
     EEGX_REQUIRE(x && out, EEGX_ERR_ARG, "nct_to_rows: NULL pointer");

@@ -23,7 +23,7 @@ template <int NVEC>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
               __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
-              long long rows, int C, float eps, int act, DropoutCfg dc) {
+              long long rows, long long rows_per_group, long long pstride, int C, float eps, int act, DropoutCfg dc) {
     EEGX_PDL_SYNC();
     const int lane = threadIdx.x & 31;
     const long long warp = (long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
@@ -61,8 +61,9 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
             const int col = (lane + 32 * i) * 8;
             if (col < C) {
                 float g[8], b[8], m[8], o[8];
-                load8f(gamma + col, g);
-                load8f(beta + col, b);
+                const long long po = (row / rows_per_group) * pstride;      // this row's parameter set
+                load8f(gamma + po + col, g);
+                load8f(beta + po + col, b);
                 gen.mask8((unsigned long long)(row * C + col) >> 3, m);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
@@ -85,12 +86,17 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
               const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean_in,
               const float* __restrict__ rstd_in, __nv_bfloat16* __restrict__ dx, float* __restrict__ part,
-              long long rows, int C, int act, DropoutCfg dc) {
+              long long rows_per_group, long long pstride, int C, int act, DropoutCfg dc) {
     EEGX_PDL_SYNC();
     __shared__ float red[LN_WARPS][LN_MAX_C];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const long long warp = (long long)blockIdx.x * LN_WARPS + wid;
     const long long nwarps = (long long)gridDim.x * LN_WARPS;
+    // blockIdx.y = parameter group: its rows, its gamma / beta, its block of partials
+    const long long row_lo = (long long)blockIdx.y * rows_per_group, rows = row_lo + rows_per_group;
+    gamma += (long long)blockIdx.y * pstride;
+    beta += (long long)blockIdx.y * pstride;
+    part += (long long)blockIdx.y * gridDim.x * 2 * C;
     const DropoutGen gen(dc);
     const float inv_c = 1.0f / (float)C;
     float dg[NVEC][8], db[NVEC][8];
@@ -99,7 +105,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
 #pragma unroll
         for (int e = 0; e < 8; ++e) dg[i][e] = db[i][e] = 0.0f;
 
-    for (long long row = warp; row < rows; row += nwarps) {
+    for (long long row = row_lo + warp; row < rows; row += nwarps) {
         const float mean = mean_in[row], rstd = rstd_in[row];
         float xh[NVEC][8], dxh[NVEC][8];
         float s1 = 0.0f, s2 = 0.0f;
@@ -168,9 +174,12 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
 // each sum every 8th block (coalesced 128-byte rows), then the warps are added in order.
 __global__ void __launch_bounds__(256)
 colsum_partials_kernel(const float* __restrict__ part, int nblocks, int nvec, int C,
-                       float* __restrict__ out0, float* __restrict__ out1, int accumulate) {
+                       float* __restrict__ out0, float* __restrict__ out1, long long out_gstride, int accumulate) {
     EEGX_PDL_SYNC();
     __shared__ float red[8][32];
+    part += (long long)blockIdx.z * nblocks * nvec * C;      // blockIdx.z = parameter group
+    out0 += (long long)blockIdx.z * out_gstride;
+    out1 += (long long)blockIdx.z * out_gstride;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + lane, j = blockIdx.y;
     float t = 0.0f;
@@ -300,6 +309,61 @@ glu_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __re
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Token assembly in front of the attention stack (layers.py:214-225):
+//   out[gb, s, :] = (s == 0 ? cls[g] : s < 4 ? temporal[g][s - 1] : h[gb, s - 4]) + pos[g][s],   g = gb / B
+// for G parameter groups of B sequences each (G = 1: a single module).  The tokens are rounded to bf16 before the
+// add, as torch.cat((tokens.to(bf16), h)) + pos does.  Backward: dh = dout[:, 4:] (below); d(pos) = column sums of
+// dout over the B sequences of a group (eegx_colsum_bf16), d(cls) / d(temporal) = its first rows.
+// ------------------------------------------------------------------------------------------
+constexpr int N_TOK = 4;
+
+__global__ void __launch_bounds__(256)
+assemble_tokens_fwd_kernel(const __nv_bfloat16* __restrict__ h, const float* __restrict__ cls, long long cls_gs,
+                           const float* __restrict__ temporal, long long tmp_gs, const float* __restrict__ pos,
+                           long long pos_gs, __nv_bfloat16* __restrict__ out, long long GB, int B, int T, int d) {
+    EEGX_PDL_SYNC();
+    const int d8 = d >> 3, S = T + N_TOK;
+    const long long total = GB * S * d8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / d8;
+        const int c = (int)(i - row * d8) * 8;
+        const long long gb = row / S;
+        const int sidx = (int)(row - gb * S);
+        const long long g = gb / B;
+        float v[8], pe[8], o[8];
+        if (sidx >= N_TOK) {
+            load8(h + (gb * T + sidx - N_TOK) * d + c, v);
+        } else {
+            if (sidx == 0) load8f(cls + g * cls_gs + c, v);
+            else load8f(temporal + g * tmp_gs + (long long)(sidx - 1) * d + c, v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __bfloat162float(__float2bfloat16(v[e]));
+        }
+        load8f(pos + g * pos_gs + (long long)sidx * d + c, pe);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = v[e] + pe[e];
+        store8(out + row * d + c, o);
+    }
+}
+
+// dh[gb, t, :] = dout[gb, t + 4, :]
+__global__ void __launch_bounds__(256)
+assemble_tokens_bwd_kernel(const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dh, long long GB, int T,
+                           int d) {
+    EEGX_PDL_SYNC();
+    const int d8 = d >> 3, S = T + N_TOK;
+    const long long total = GB * T * d8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / d8;
+        const int c = (int)(i - row * d8) * 8;
+        const long long gb = row / T;
+        const int t = (int)(row - gb * T);
+        *reinterpret_cast<uint4*>(dh + row * d + c) =
+            *reinterpret_cast<const uint4*>(dout + (gb * S + t + N_TOK) * d + c);
+    }
+}
+
 int ew_grid(long long n8) {
     long long b = (n8 + 255) / 256;
     const long long cap = (long long)kNumSMsB200 * 8;
@@ -309,27 +373,29 @@ int ew_grid(long long n8) {
 // forward: one row per warp, as many CTAs as rows allow (memory bound: occupancy matters);
 // backward: capped, every CTA leaves a (2, C) partial for the fixed-order finalize.
 constexpr int LN_BWD_CTAS_PER_SM = 2;
-int ln_grid(long long rows, bool bwd) {
+int ln_grid(long long rows, bool bwd, int groups = 1) {     // CTAs per group (backward) / in total (forward)
     long long b = (rows + LN_WARPS - 1) / LN_WARPS;
-    const long long cap = (long long)kNumSMsB200 * (bwd ? LN_BWD_CTAS_PER_SM : 16);
+    long long cap = (long long)kNumSMsB200 * (bwd ? LN_BWD_CTAS_PER_SM : 16);
+    if (bwd) cap = cap / groups < 1 ? 1 : cap / groups;
     return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
 template <int NVEC>
 void launch_ln_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
-                   long long rows, int C, float eps, int act, DropoutCfg dc, cudaStream_t st) {
-    eegx::launch(ln_fwd_kernel<NVEC>, ln_grid(rows, false), LN_WARPS * 32, 0, st, 
-        static_cast<const __nv_bfloat16*>(x), gamma, beta, static_cast<__nv_bfloat16*>(y), mean, rstd, rows, C, eps,
-        act, dc);
+                   long long rows, long long rpg, long long pstride, int C, float eps, int act, DropoutCfg dc,
+                   cudaStream_t st) {
+    eegx::launch(ln_fwd_kernel<NVEC>, ln_grid(rows, false), LN_WARPS * 32, 0, st,
+        static_cast<const __nv_bfloat16*>(x), gamma, beta, static_cast<__nv_bfloat16*>(y), mean, rstd, rows, rpg, pstride,
+        C, eps, act, dc);
 }
 
 template <int NVEC>
 void launch_ln_bwd(const void* dy, const void* x, const float* gamma, const float* beta, const float* mean,
-                   const float* rstd, void* dx, float* part, int grid, long long rows, int C, int act,
-                   DropoutCfg dc, cudaStream_t st) {
-    eegx::launch(ln_bwd_kernel<NVEC>, grid, LN_WARPS * 32, 0, st, 
+                   const float* rstd, void* dx, float* part, int grid, int groups, long long rpg, long long pstride,
+                   int C, int act, DropoutCfg dc, cudaStream_t st) {
+    eegx::launch(ln_bwd_kernel<NVEC>, dim3((unsigned)grid, (unsigned)groups), LN_WARPS * 32, 0, st,
         static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), gamma, beta, mean, rstd,
-        static_cast<__nv_bfloat16*>(dx), part, rows, C, act, dc);
+        static_cast<__nv_bfloat16*>(dx), part, rpg, pstride, C, act, dc);
 }
 
 }  // namespace
@@ -341,12 +407,15 @@ void launch_ln_bwd(const void* dy, const void* x, const float* gamma, const floa
 extern "C" {
 
 int eegx_layernorm_fwd_bf16(const void* x, const float* gamma, const float* beta, void* y, float* mean,
-                            float* rstd, int64_t rows, int64_t C, float eps, int act, const uint64_t* rng_state,
-                            uint32_t site, float p, void* stream) {
+                            float* rstd, int64_t rows, int64_t C, int64_t groups, int64_t param_stride, float eps, int act,
+                            const uint64_t* rng_state, uint32_t site, float p, void* stream) {
     if (int rc = eegx::require_sm100()) return rc;
     EEGX_REQUIRE(rows >= 0 && C >= 8 && C <= LN_MAX_C && (C % 8) == 0, EEGX_ERR_SHAPE,
                  "layernorm: C must be a multiple of 8 in [8, %d]", LN_MAX_C);
+    EEGX_REQUIRE(groups >= 1 && rows % groups == 0 && (param_stride % 4) == 0, EEGX_ERR_SHAPE,
+                 "layernorm: rows must split evenly over the groups; parameter stride a multiple of 4");
     if (rows == 0) return EEGX_OK;
+    const long long rpg = rows / groups, ps = groups > 1 ? param_stride : 0;
     EEGX_REQUIRE(x && gamma && beta && y && mean && rstd, EEGX_ERR_ARG, "layernorm: NULL pointer");
     EEGX_REQUIRE(eegx::aligned16(x) && eegx::aligned16(y) && eegx::aligned16(gamma) && eegx::aligned16(beta),
                  EEGX_ERR_ALIGN, "layernorm: pointers must be 16-byte aligned");
@@ -354,12 +423,12 @@ int eegx_layernorm_fwd_bf16(const void* x, const float* gamma, const float* beta
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int nvec = (int)((C + 255) / 256);
     switch (nvec) {
-        case 1: launch_ln_fwd<1>(x, gamma, beta, y, mean, rstd, rows, (int)C, eps, act, dc, st); break;
-        case 2: launch_ln_fwd<2>(x, gamma, beta, y, mean, rstd, rows, (int)C, eps, act, dc, st); break;
-        case 3: launch_ln_fwd<3>(x, gamma, beta, y, mean, rstd, rows, (int)C, eps, act, dc, st); break;
-        case 4: launch_ln_fwd<4>(x, gamma, beta, y, mean, rstd, rows, (int)C, eps, act, dc, st); break;
-        case 5: case 6: launch_ln_fwd<6>(x, gamma, beta, y, mean, rstd, rows, (int)C, eps, act, dc, st); break;
-        default: launch_ln_fwd<8>(x, gamma, beta, y, mean, rstd, rows, (int)C, eps, act, dc, st); break;
+        case 1: launch_ln_fwd<1>(x, gamma, beta, y, mean, rstd, rows, rpg, ps, (int)C, eps, act, dc, st); break;
+        case 2: launch_ln_fwd<2>(x, gamma, beta, y, mean, rstd, rows, rpg, ps, (int)C, eps, act, dc, st); break;
+        case 3: launch_ln_fwd<3>(x, gamma, beta, y, mean, rstd, rows, rpg, ps, (int)C, eps, act, dc, st); break;
+        case 4: launch_ln_fwd<4>(x, gamma, beta, y, mean, rstd, rows, rpg, ps, (int)C, eps, act, dc, st); break;
+        case 5: case 6: launch_ln_fwd<6>(x, gamma, beta, y, mean, rstd, rows, rpg, ps, (int)C, eps, act, dc, st); break;
+        default: launch_ln_fwd<8>(x, gamma, beta, y, mean, rstd, rows, rpg, ps, (int)C, eps, act, dc, st); break;
     }
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
@@ -372,10 +441,14 @@ size_t eegx_layernorm_bwd_workspace_bytes(int64_t C) {
 int eegx_layernorm_bwd_bf16(const void* dy, const void* x, const float* gamma, const float* beta,
                             const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
                             int accumulate, void* workspace, size_t workspace_bytes, int64_t rows, int64_t C,
-                            int act, const uint64_t* rng_state, uint32_t site, float p, void* stream) {
+                            int64_t groups, int64_t param_stride, int act, const uint64_t* rng_state, uint32_t site,
+                            float p, void* stream) {
     if (int rc = eegx::require_sm100()) return rc;
     EEGX_REQUIRE(rows >= 0 && C >= 8 && C <= LN_MAX_C && (C % 8) == 0, EEGX_ERR_SHAPE,
                  "layernorm: C must be a multiple of 8 in [8, %d]", LN_MAX_C);
+    EEGX_REQUIRE(groups >= 1 && groups <= kNumSMsB200 && rows % groups == 0 && (param_stride % 4) == 0, EEGX_ERR_SHAPE,
+                 "layernorm bwd: rows must split evenly over the groups; parameter stride a multiple of 4");
+    const long long rpg = rows / groups, ps = groups > 1 ? param_stride : 0;
     EEGX_REQUIRE(dy && x && gamma && beta && mean && rstd && dx && dgamma && dbeta && workspace, EEGX_ERR_ARG,
                  "layernorm bwd: NULL pointer");
     EEGX_REQUIRE(workspace_bytes >= eegx_layernorm_bwd_workspace_bytes(C), EEGX_ERR_WORKSPACE,
@@ -384,18 +457,19 @@ int eegx_layernorm_bwd_bf16(const void* dy, const void* x, const float* gamma, c
                      eegx::aligned16(beta), EEGX_ERR_ALIGN, "layernorm bwd: pointers must be 16-byte aligned");
     const DropoutCfg dc{reinterpret_cast<const unsigned long long*>(rng_state), site, p};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int grid = ln_grid(rows, true);
+    const int grid = ln_grid(rpg, true, (int)groups);
     float* part = static_cast<float*>(workspace);
     const int nvec = (int)((C + 255) / 256);
     switch (nvec) {
-        case 1: launch_ln_bwd<1>(dy, x, gamma, beta, mean, rstd, dx, part, grid, rows, (int)C, act, dc, st); break;
-        case 2: launch_ln_bwd<2>(dy, x, gamma, beta, mean, rstd, dx, part, grid, rows, (int)C, act, dc, st); break;
-        case 3: launch_ln_bwd<3>(dy, x, gamma, beta, mean, rstd, dx, part, grid, rows, (int)C, act, dc, st); break;
-        case 4: launch_ln_bwd<4>(dy, x, gamma, beta, mean, rstd, dx, part, grid, rows, (int)C, act, dc, st); break;
-        case 5: case 6: launch_ln_bwd<6>(dy, x, gamma, beta, mean, rstd, dx, part, grid, rows, (int)C, act, dc, st); break;
-        default: launch_ln_bwd<8>(dy, x, gamma, beta, mean, rstd, dx, part, grid, rows, (int)C, act, dc, st); break;
+        case 1: launch_ln_bwd<1>(dy, x, gamma, beta, mean, rstd, dx, part, grid, (int)groups, rpg, ps, (int)C, act, dc, st); break;
+        case 2: launch_ln_bwd<2>(dy, x, gamma, beta, mean, rstd, dx, part, grid, (int)groups, rpg, ps, (int)C, act, dc, st); break;
+        case 3: launch_ln_bwd<3>(dy, x, gamma, beta, mean, rstd, dx, part, grid, (int)groups, rpg, ps, (int)C, act, dc, st); break;
+        case 4: launch_ln_bwd<4>(dy, x, gamma, beta, mean, rstd, dx, part, grid, (int)groups, rpg, ps, (int)C, act, dc, st); break;
+        case 5: case 6: launch_ln_bwd<6>(dy, x, gamma, beta, mean, rstd, dx, part, grid, (int)groups, rpg, ps, (int)C, act, dc, st); break;
+        default: launch_ln_bwd<8>(dy, x, gamma, beta, mean, rstd, dx, part, grid, (int)groups, rpg, ps, (int)C, act, dc, st); break;
     }
-    eegx::launch(colsum_partials_kernel, dim3((unsigned)((C + 31) / 32), 2), 256, 0, st, part, grid, 2, (int)C, dgamma, dbeta, accumulate);
+    eegx::launch(colsum_partials_kernel, dim3((unsigned)((C + 31) / 32), 2, (unsigned)groups), 256, 0, st, part, grid, 2, (int)C,
+                 dgamma, dbeta, ps, accumulate);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
 }
@@ -484,6 +558,36 @@ int eegx_glu_bwd_bf16(const void* dout, const void* ag, void* dag, int64_t rows,
     eegx::launch(glu_bwd_kernel, ew_grid(rows * (H / 8)), 256, 0, static_cast<cudaStream_t>(stream), 
         static_cast<const __nv_bfloat16*>(dout), static_cast<const __nv_bfloat16*>(ag),
         static_cast<__nv_bfloat16*>(dag), rows, (int)H, dc);
+    EEGX_CUDA_CHECK(cudaGetLastError());
+    return EEGX_OK;
+}
+
+int eegx_assemble_tokens_fwd_bf16(const void* h, const float* cls, int64_t cls_gstride, const float* temporal,
+                                  int64_t temporal_gstride, const float* pos, int64_t pos_gstride, void* out, int64_t G,
+                                  int64_t B, int64_t T, int64_t d, void* stream) {
+    if (int rc = eegx::require_sm100()) return rc;
+    EEGX_REQUIRE(G >= 1 && B >= 0 && T >= 1 && d >= 8 && (d % 8) == 0, EEGX_ERR_SHAPE,
+                 "assemble_tokens: need G >= 1, T >= 1, d a multiple of 8");
+    if (B == 0) return EEGX_OK;
+    EEGX_REQUIRE(h && cls && temporal && pos && out, EEGX_ERR_ARG, "assemble_tokens: NULL pointer");
+    EEGX_REQUIRE(eegx::aligned16(h) && eegx::aligned16(out) && eegx::aligned16(cls) && eegx::aligned16(temporal) &&
+                     eegx::aligned16(pos) && (cls_gstride % 4) == 0 && (temporal_gstride % 4) == 0 && (pos_gstride % 4) == 0,
+                 EEGX_ERR_ALIGN, "assemble_tokens: pointers and group strides must be 16-byte aligned");
+    eegx::launch(assemble_tokens_fwd_kernel, ew_grid(G * B * (T + N_TOK) * (d / 8)), 256, 0, static_cast<cudaStream_t>(stream),
+                 static_cast<const __nv_bfloat16*>(h), cls, (long long)cls_gstride, temporal, (long long)temporal_gstride, pos,
+                 (long long)pos_gstride, static_cast<__nv_bfloat16*>(out), (long long)(G * B), (int)B, (int)T, (int)d);
+    EEGX_CUDA_CHECK(cudaGetLastError());
+    return EEGX_OK;
+}
+
+int eegx_assemble_tokens_bwd_bf16(const void* dout, void* dh, int64_t GB, int64_t T, int64_t d, void* stream) {
+    if (int rc = eegx::require_sm100()) return rc;
+    EEGX_REQUIRE(GB >= 0 && T >= 1 && d >= 8 && (d % 8) == 0, EEGX_ERR_SHAPE, "assemble_tokens bwd: bad sizes");
+    if (GB == 0) return EEGX_OK;
+    EEGX_REQUIRE(dout && dh, EEGX_ERR_ARG, "assemble_tokens bwd: NULL pointer");
+    EEGX_REQUIRE(eegx::aligned16(dout) && eegx::aligned16(dh), EEGX_ERR_ALIGN, "assemble_tokens bwd: 16-byte alignment");
+    eegx::launch(assemble_tokens_bwd_kernel, ew_grid(GB * T * (d / 8)), 256, 0, static_cast<cudaStream_t>(stream),
+                 static_cast<const __nv_bfloat16*>(dout), static_cast<__nv_bfloat16*>(dh), (long long)GB, (int)T, (int)d);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
 }

@@ -34,8 +34,11 @@ constexpr int NUM_EPI_WARPS = 4;
 constexpr unsigned WATCHDOG_SPINS = 1u << 27;
 
 struct GemmParams {
-    long long M, N, K, batch;
-    long long ldd, stride_d;
+    long long M, N, K, batch;      // batch = inner * groups problems; problem bi = (g = bi / inner, s = bi % inner)
+    long long inner;               // problems per group (split-K chunks); 1 for a plain grouped launch
+    long long ldd, stride_d;       // D: row pitch, stride between the `inner` problems of a group
+    long long stride_d_g;          // D stride between groups
+    long long stride_bias_g;       // bias stride between groups (0: one bias for all)
     const float* bias;
     void* D;
     int out_f32;
@@ -75,11 +78,12 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     }
 }
 
-__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, unsigned bar, int c0,
-                                            int c1, int c2) {
+// 4-D operand maps: (inner dim, rows, problem inside the group, group)
+__device__ __forceinline__ void tma_load_4d(unsigned dst, const CUtensorMap* map, unsigned bar, int c0,
+                                            int c1, int c2, int c3) {
     asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
 
@@ -159,20 +163,21 @@ constexpr int EPI_WARP_BYTES = 32 * EPI_ROW_BYTES;       // 4608
 constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_WARP_BYTES;
 
 // alpha / bias / GELU on one 32-column chunk of this lane's row
-__device__ __forceinline__ void epilogue_math(const GemmParams& p, const unsigned (&r)[32], float (&v)[32], long long col0) {
+__device__ __forceinline__ void epilogue_math(const GemmParams& p, const float* __restrict__ bias, const unsigned (&r)[32],
+                                              float (&v)[32], long long col0) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
     if (p.epilogue >= 1) {
-        if (col0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
+        if (col0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(bias) & 15) == 0) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + i));
                 v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
             }
         } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-                if (col0 + i < p.N) v[i] += __ldg(p.bias + col0 + i);
+                if (col0 + i < p.N) v[i] += __ldg(bias + col0 + i);
         }
     }
     if (p.epilogue == 2) {
@@ -183,9 +188,9 @@ __device__ __forceinline__ void epilogue_math(const GemmParams& p, const unsigne
 
 // scalar fallback: this lane writes its own row (unaligned D / ragged N)
 __device__ __forceinline__ void epilogue_store_direct(const GemmParams& p, const float (&v)[32], bool row_ok, long long row,
-                                                      long long col0, long long bi) {
+                                                      long long col0, long long d_off) {
     if (!row_ok || col0 >= p.N) return;
-    const long long off = bi * p.stride_d + row * p.ldd + col0;
+    const long long off = d_off + row * p.ldd + col0;
     if (p.out_f32) {
         float* d = reinterpret_cast<float*>(p.D) + off;
         for (int i = 0; i < 32; ++i)
@@ -223,13 +228,13 @@ __device__ __forceinline__ void patch_write(unsigned char* patch, int lane, int 
 // chain per row exposed eight global-memory latencies per chunk and made the small weight-gradient GEMMs,
 // which accumulate straight into the gradient buffers, ~3x slower than their forward twins).
 __device__ __forceinline__ void patch_flush(const GemmParams& p, const unsigned char* patch, int lane, long long row0,
-                                            long long col0, long long bi) {
+                                            long long col0, long long d_off) {
     const int piece = lane & 7;
     const int epp = p.out_f32 ? 4 : 8;                   // elements per 16-byte piece
     const long long col = col0 + piece * epp;
     const bool col_ok = col < p.N;
     const size_t es = p.out_f32 ? 4 : 2;
-    unsigned char* base = static_cast<unsigned char*>(p.D) + (size_t)(bi * p.stride_d + col) * es;
+    unsigned char* base = static_cast<unsigned char*>(p.D) + (size_t)(d_off + col) * es;
     uint4 old[8];
     if (p.accumulate) {
 #pragma unroll
@@ -269,6 +274,9 @@ __device__ __forceinline__ void patch_flush(const GemmParams& p, const unsigned 
 template <int BLOCK_N>
 __device__ __forceinline__ void epilogue_rows(const GemmParams& p, unsigned taddr, long long row0, int lane, long long n_base,
                                               long long bi, unsigned char* patch) {
+    const long long grp = bi / p.inner;
+    const long long d_off = grp * p.stride_d_g + (bi - grp * p.inner) * p.stride_d;     // element offset of this problem's D
+    const float* bias = p.bias + grp * p.stride_bias_g;
     constexpr int NC = BLOCK_N / 32;
     static_assert(NC % 2 == 0, "BLOCK_N must be a multiple of 64");
     if (p.debug == 2) return;
@@ -283,29 +291,29 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, unsigned tadd
     for (int c = 0; c < NC; c += 2) {
         tmem_ld32_issue(taddr + (c + 1) * 32, r1);
         const long long col0 = n_base + c * 32;
-        epilogue_math(p, r0, v, col0);
+        epilogue_math(p, bias, r0, v, col0);
         if (p.debug != 1) {
             if (!p.vec_ok) {
-                epilogue_store_direct(p, v, row_ok, row, col0, bi);
+                epilogue_store_direct(p, v, row_ok, row, col0, d_off);
             } else {
                 patch_write(patch, lane, 0, v, f32);
                 if (f32) {
                     __syncwarp();
-                    patch_flush(p, patch, lane, row0, col0, bi);
+                    patch_flush(p, patch, lane, row0, col0, d_off);
                     __syncwarp();
                 }
             }
         }
         tmem_ld_wait(r1);
         if (c + 2 < NC) tmem_ld32_issue(taddr + (c + 2) * 32, r0);
-        epilogue_math(p, r1, v, col0 + 32);
+        epilogue_math(p, bias, r1, v, col0 + 32);
         if (p.debug != 1) {
             if (!p.vec_ok) {
-                epilogue_store_direct(p, v, row_ok, row, col0 + 32, bi);
+                epilogue_store_direct(p, v, row_ok, row, col0 + 32, d_off);
             } else {
                 patch_write(patch, lane, f32 ? 0 : 64, v, f32);
                 __syncwarp();
-                patch_flush(p, patch, lane, row0, f32 ? col0 + 32 : col0, bi);
+                patch_flush(p, patch, lane, row0, f32 ? col0 + 32 : col0, d_off);
                 __syncwarp();
             }
         }
@@ -379,26 +387,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 const long long bi = tile / tiles_per_batch;
                 const long long rem = tile - bi * tiles_per_batch;
                 const int n_blk = (int)(rem / m_blocks), m_blk = (int)(rem % m_blocks);   // m fastest: B tile stays hot in L2
+                const int cg = (int)(bi / p.inner), cs = (int)(bi - (long long)cg * p.inner);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const unsigned a_dst = smem_base + stage * L::STAGE_BYTES;
                     const unsigned b_dst = a_dst + L::A_BYTES;
                     mbar_expect_tx(full_bar(stage), L::STAGE_BYTES);
                     if (!A_MN) {
-                        tma_load_3d(a_dst, &map_a, full_bar(stage), kb * BLOCK_K, m_blk * BLOCK_M, (int)bi);
+                        tma_load_4d(a_dst, &map_a, full_bar(stage), kb * BLOCK_K, m_blk * BLOCK_M, cs, cg);
                     } else {
 #pragma unroll
                         for (int h = 0; h < BLOCK_M / 64; ++h)
-                            tma_load_3d(a_dst + h * (64 * BLOCK_K * 2), &map_a, full_bar(stage),
-                                        m_blk * BLOCK_M + h * 64, kb * BLOCK_K, (int)bi);
+                            tma_load_4d(a_dst + h * (64 * BLOCK_K * 2), &map_a, full_bar(stage),
+                                        m_blk * BLOCK_M + h * 64, kb * BLOCK_K, cs, cg);
                     }
                     if (!B_MN) {
-                        tma_load_3d(b_dst, &map_b, full_bar(stage), kb * BLOCK_K, n_blk * BLOCK_N, (int)bi);
+                        tma_load_4d(b_dst, &map_b, full_bar(stage), kb * BLOCK_K, n_blk * BLOCK_N, cs, cg);
                     } else {
 #pragma unroll
                         for (int h = 0; h < BLOCK_N / 64; ++h)
-                            tma_load_3d(b_dst + h * (64 * BLOCK_K * 2), &map_b, full_bar(stage),
-                                        n_blk * BLOCK_N + h * 64, kb * BLOCK_K, (int)bi);
+                            tma_load_4d(b_dst + h * (64 * BLOCK_K * 2), &map_b, full_bar(stage),
+                                        n_blk * BLOCK_N + h * 64, kb * BLOCK_K, cs, cg);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -491,12 +500,12 @@ __device__ __forceinline__ unsigned cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tma_load_3d_2sm(unsigned dst, const CUtensorMap* map, unsigned leader_bar, int c0,
-                                                int c1, int c2) {
+__device__ __forceinline__ void tma_load_4d_2sm(unsigned dst, const CUtensorMap* map, unsigned leader_bar, int c0,
+                                                int c1, int c2, int c3) {
     asm volatile(
-        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-        " [%0], [%1, {%3, %4, %5}], [%2], %6;"
-        ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2),
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
           "l"(0x1000000000000000ull)
         : "memory");
 }
@@ -599,6 +608,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const int n_blk = (int)(rem / m_blocks), m_blk = (int)(rem % m_blocks);
                 const int m0 = m_blk * 2 * BLOCK_M + (int)rank * BLOCK_M;
                 const int n0 = n_blk * BLOCK_N + (int)rank * HALF_N;
+                const int cg = (int)(bi / p.inner), cs = (int)(bi - (long long)cg * p.inner);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const unsigned a_dst = smem_base + stage * L::STAGE_BYTES;
@@ -606,18 +616,18 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     const unsigned lead_full = full_bar(stage) & 0xFEFFFFFFu;     // the leader's barrier (peer bit cleared)
                     if (leader) mbar_expect_tx(full_bar(stage), 2 * L::STAGE_BYTES);
                     if (!A_MN) {
-                        tma_load_3d_2sm(a_dst, &map_a, lead_full, kb * BLOCK_K, m0, (int)bi);
+                        tma_load_4d_2sm(a_dst, &map_a, lead_full, kb * BLOCK_K, m0, cs, cg);
                     } else {
 #pragma unroll
                         for (int h = 0; h < BLOCK_M / 64; ++h)
-                            tma_load_3d_2sm(a_dst + h * (64 * BLOCK_K * 2), &map_a, lead_full, m0 + h * 64, kb * BLOCK_K, (int)bi);
+                            tma_load_4d_2sm(a_dst + h * (64 * BLOCK_K * 2), &map_a, lead_full, m0 + h * 64, kb * BLOCK_K, cs, cg);
                     }
                     if (!B_MN) {
-                        tma_load_3d_2sm(b_dst, &map_b, lead_full, kb * BLOCK_K, n0, (int)bi);
+                        tma_load_4d_2sm(b_dst, &map_b, lead_full, kb * BLOCK_K, n0, cs, cg);
                     } else {
 #pragma unroll
                         for (int h = 0; h < HALF_N / 64; ++h)
-                            tma_load_3d_2sm(b_dst + h * (64 * BLOCK_K * 2), &map_b, lead_full, n0 + h * 64, kb * BLOCK_K, (int)bi);
+                            tma_load_4d_2sm(b_dst + h * (64 * BLOCK_K * 2), &map_b, lead_full, n0 + h * 64, kb * BLOCK_K, cs, cg);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -708,20 +718,22 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 3-D bf16 tensor map: dims (inner, rows, batch); box (box_inner, box_rows, 1); 128B swizzle.
-int make_map(CUtensorMap* map, const void* base, long long inner, long long rows, long long batch,
-             long long ld_elems, long long batch_stride_elems, int box_inner, int box_rows) {
+// 4-D bf16 tensor map: dims (inner, rows, batch, groups); box (box_inner, box_rows, 1, 1); 128B swizzle.
+int make_map(CUtensorMap* map, const void* base, long long inner, long long rows, long long batch, long long groups,
+             long long ld_elems, long long batch_stride_elems, long long group_stride_elems, int box_inner, int box_rows) {
     EncodeTiledFn enc = get_encode_fn();
     EEGX_REQUIRE(enc != nullptr, EEGX_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
-    cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)batch};
-    cuuint64_t strides[2] = {(cuuint64_t)ld_elems * 2, (cuuint64_t)(batch > 1 ? batch_stride_elems : ld_elems * rows) * 2};
-    cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+    const long long bs = batch > 1 ? batch_stride_elems : ld_elems * rows;        // size-1 dims still need a legal stride
+    const long long gs = groups > 1 ? group_stride_elems : bs * batch;
+    cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)batch, (cuuint64_t)groups};
+    cuuint64_t strides[3] = {(cuuint64_t)ld_elems * 2, (cuuint64_t)bs * 2, (cuuint64_t)gs * 2};
+    cuuint32_t box[4] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     EEGX_REQUIRE(r == CUDA_SUCCESS, EEGX_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d "
-                 "(inner=%lld rows=%lld batch=%lld ld=%lld)", (int)r, inner, rows, batch, ld_elems);
+                 "(inner=%lld rows=%lld batch=%lld groups=%lld ld=%lld)", (int)r, inner, rows, batch, groups, ld_elems);
     return EEGX_OK;
 }
 
@@ -778,6 +790,10 @@ extern "C" int eegx_gemm_bf16(const eegx_gemm_desc* d, const void* A, const void
                  "A, B, D must be 16-byte aligned");
     EEGX_REQUIRE((d->lda % 8) == 0 && (d->ldb % 8) == 0 && (d->stride_a % 8) == 0 && (d->stride_b % 8) == 0,
                  EEGX_ERR_ALIGN, "lda/ldb/batch strides must be multiples of 8 elements (TMA: 16 bytes)");
+    const long long groups = d->groups > 1 ? d->groups : 1;
+    EEGX_REQUIRE(d->groups >= 0 && (groups == 1 || ((d->stride_a_g % 8) == 0 && (d->stride_b_g % 8) == 0)), EEGX_ERR_ALIGN,
+                 "group strides must be multiples of 8 elements (TMA: 16 bytes)");
+    const long long problems = d->batch * groups;
     // lda / ldb may be SMALLER than the contiguous extent: rows then overlap in memory, which is
     // how a channels-last Conv1d runs as an implicit-im2col GEMM (row r = k consecutive time steps).
     EEGX_REQUIRE(d->lda >= 8 && d->ldb >= 8 && d->ldd >= d->N, EEGX_ERR_SHAPE,
@@ -791,7 +807,7 @@ extern "C" int eegx_gemm_bf16(const eegx_gemm_desc* d, const void* A, const void
     const bool bm_ = d->b_mn_major != 0;
     auto rounds_for = [&](int bn, bool pr) {
         const long long mb_ = pr ? (d->M + 2 * BLOCK_M - 1) / (2 * BLOCK_M) : (d->M + BLOCK_M - 1) / BLOCK_M;
-        const long long t = mb_ * ((d->N + bn - 1) / bn) * d->batch;
+        const long long t = mb_ * ((d->N + bn - 1) / bn) * problems;
         const long long slots = pr ? eegx::kNumSMsB200 / 2 : eegx::kNumSMsB200;
         return (double)((t + slots - 1) / slots);
     };
@@ -823,16 +839,18 @@ extern "C" int eegx_gemm_bf16(const eegx_gemm_desc* d, const void* A, const void
 
     CUtensorMap ma, mb;
     int rc;
-    if (!d->a_mn_major) rc = make_map(&ma, A, d->K, d->M, d->batch, d->lda, d->stride_a, BLOCK_K, BLOCK_M);
-    else rc = make_map(&ma, A, d->M, d->K, d->batch, d->lda, d->stride_a, 64, BLOCK_K);
+    if (!d->a_mn_major) rc = make_map(&ma, A, d->K, d->M, d->batch, groups, d->lda, d->stride_a, d->stride_a_g, BLOCK_K, BLOCK_M);
+    else rc = make_map(&ma, A, d->M, d->K, d->batch, groups, d->lda, d->stride_a, d->stride_a_g, 64, BLOCK_K);
     if (rc) return rc;
-    if (!d->b_mn_major) rc = make_map(&mb, B, d->K, d->N, d->batch, d->ldb, d->stride_b, BLOCK_K, b_box_rows);
-    else rc = make_map(&mb, B, d->N, d->K, d->batch, d->ldb, d->stride_b, 64, BLOCK_K);
+    if (!d->b_mn_major) rc = make_map(&mb, B, d->K, d->N, d->batch, groups, d->ldb, d->stride_b, d->stride_b_g, BLOCK_K, b_box_rows);
+    else rc = make_map(&mb, B, d->N, d->K, d->batch, groups, d->ldb, d->stride_b, d->stride_b_g, 64, BLOCK_K);
     if (rc) return rc;
 
     GemmParams p;
-    p.M = d->M; p.N = d->N; p.K = d->K; p.batch = d->batch;
+    p.M = d->M; p.N = d->N; p.K = d->K; p.batch = problems; p.inner = d->batch;
     p.ldd = d->ldd; p.stride_d = d->stride_d;
+    p.stride_d_g = groups > 1 ? d->stride_d_g : 0;
+    p.stride_bias_g = groups > 1 ? d->stride_bias_g : 0;
     p.bias = bias; p.D = D;
     p.out_f32 = d->out_f32; p.epilogue = d->epilogue; p.accumulate = d->accumulate;
     p.alpha = d->alpha;
@@ -840,7 +858,8 @@ extern "C" int eegx_gemm_bf16(const eegx_gemm_desc* d, const void* A, const void
     p.debug = env_debug;
     {
         const long long es = d->out_f32 ? 4 : 2, epp = 16 / es;
-        p.vec_ok = (d->ldd % epp) == 0 && (d->N % epp) == 0 && (d->batch == 1 || (d->stride_d % epp) == 0);
+        p.vec_ok = (d->ldd % epp) == 0 && (d->N % epp) == 0 && (d->batch == 1 || (d->stride_d % epp) == 0) &&
+                   (groups == 1 || (d->stride_d_g % epp) == 0);
     }
 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -848,7 +867,7 @@ extern "C" int eegx_gemm_bf16(const eegx_gemm_desc* d, const void* A, const void
     const long long n_blocks = (d->N + block_n - 1) / block_n;
     if (pair) {
         const long long m_blocks2 = (d->M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
-        const long long tiles2 = m_blocks2 * n_blocks * d->batch;
+        const long long tiles2 = m_blocks2 * n_blocks * problems;
         const long long max_clusters = eegx::kNumSMsB200 / 2;
         const int grid2 = 2 * (int)(tiles2 < max_clusters ? tiles2 : max_clusters);
         if (block_n == 128) return dispatch_major2<128, 8>(am, bm, ma, mb, p, grid2, st);
@@ -859,7 +878,7 @@ extern "C" int eegx_gemm_bf16(const eegx_gemm_desc* d, const void* A, const void
         return dispatch_major2<256, 6>(am, bm, ma, mb, p, grid2, st);
     }
     const long long m_blocks = (d->M + BLOCK_M - 1) / BLOCK_M;
-    const long long tiles = m_blocks * n_blocks * d->batch;
+    const long long tiles = m_blocks * n_blocks * problems;
     const int grid = (int)(tiles < eegx::kNumSMsB200 ? tiles : eegx::kNumSMsB200);
     switch (block_n) {
         case 64: return dispatch_major<64, 8>(am, bm, ma, mb, p, grid, st);

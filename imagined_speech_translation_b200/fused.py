@@ -115,7 +115,7 @@ def colsum(y: torch.Tensor, into: Optional[torch.Tensor] = None) -> Optional[tor
         return None if into is not None else out.zero_()
     lib = _lib.lib()
     ws = _workspace(lib.eegx_colreduce_workspace_bytes(C_), y.device)
-    _lib.check(lib.eegx_colsum_bf16(_lib.ptr(y), y.stride(0), rows, C_, _lib.ptr(out), int(into is not None),
+    _lib.check(lib.eegx_colsum_bf16(_lib.ptr(y), y.stride(0), 1, 0, rows, C_, _lib.ptr(out), 0, int(into is not None),
                                     _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "eegx_colsum_bf16")
     return None if into is not None else out
 
@@ -123,7 +123,7 @@ def colsum(y: torch.Tensor, into: Optional[torch.Tensor] = None) -> Optional[tor
 def accumulate_partials(part: torch.Tensor, into: torch.Tensor) -> None:
     """into += part.sum(0) for fp32 split-K partials (s, ...) in one pass."""
     s = part.shape[0]
-    _lib.check(_lib.lib().eegx_accumulate_partials_f32(_lib.ptr(part), s, part.numel() // s, _lib.ptr(into), 1,
+    _lib.check(_lib.lib().eegx_accumulate_partials_f32(_lib.ptr(part), s, 1, part.numel() // s, _lib.ptr(into), 0, 1,
                                                        _lib.stream_ptr()), "eegx_accumulate_partials_f32")
 
 
@@ -146,7 +146,7 @@ class _LayerNorm(torch.autograd.Function):
         rstd = torch.empty_like(mean)
         w, b = _f32(weight), _f32(bias)
         _lib.check(_lib.lib().eegx_layernorm_fwd_bf16(
-            _lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(y), _lib.ptr(mean), _lib.ptr(rstd), rows, C_,
+            _lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(y), _lib.ptr(mean), _lib.ptr(rstd), rows, C_, 1, 0,
             float(eps), int(act), _lib.ptr(rng), site, p, _lib.stream_ptr()), "eegx_layernorm_fwd_bf16")
         ctx.save_for_backward(x, weight, bias, mean, rstd)
         ctx.cfg = (int(act), rng, site, p)
@@ -168,7 +168,7 @@ class _LayerNorm(torch.autograd.Function):
         ws = _workspace(lib.eegx_layernorm_bwd_workspace_bytes(C_), x.device)
         _lib.check(lib.eegx_layernorm_bwd_bf16(
             _lib.ptr(dy), _lib.ptr(x), _lib.ptr(_f32(weight)), _lib.ptr(_f32(bias)), _lib.ptr(mean), _lib.ptr(rstd),
-            _lib.ptr(dx), _lib.ptr(dg), _lib.ptr(db), int(fused_acc), _lib.ptr(ws), ws.numel(), rows, C_, act,
+            _lib.ptr(dx), _lib.ptr(dg), _lib.ptr(db), int(fused_acc), _lib.ptr(ws), ws.numel(), rows, C_, 1, 0, act,
             _lib.ptr(rng), site, p, _lib.stream_ptr()), "eegx_layernorm_bwd_bf16")
         if fused_acc:
             return dx, None, None, None, None, None, None, None
@@ -318,8 +318,8 @@ def _bn_stats(yg, bn, B, T, training):
     ws = _workspace(lib.eegx_colreduce_workspace_bytes(C_), yg.device)
     track = bn.track_running_stats and bn.running_mean is not None
     _lib.check(lib.eegx_bn_stats_bf16(
-        _lib.ptr(yg[PAD:]), B, T, PAD, C_, float(bn.eps), _lib.ptr(mean), _lib.ptr(rstd),
-        _lib.ptr(bn.running_mean) if track else None, _lib.ptr(bn.running_var) if track else None,
+        _lib.ptr(yg[PAD:]), 1, B, T, PAD, C_, float(bn.eps), _lib.ptr(mean), _lib.ptr(rstd),
+        _lib.ptr(bn.running_mean) if track else None, _lib.ptr(bn.running_var) if track else None, 0,
         float(bn.momentum if bn.momentum is not None else 0.1), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
         "eegx_bn_stats_bf16")
     if track:
@@ -348,7 +348,7 @@ class _BnAct(torch.autograd.Function):
         _lib.check(_lib.lib().eegx_bn_act_fwd_bf16(
             _lib.ptr(ya[PAD:]), _lib.ptr(mean_a), _lib.ptr(rstd_a), _lib.ptr(ga), _lib.ptr(ba),
             _lib.ptr(yr[PAD:]) if res_mode else None, _lib.ptr(mean_r), _lib.ptr(rstd_r), _lib.ptr(gr), _lib.ptr(br),
-            res_mode, _lib.ptr(out[PAD:]), B, T, PAD, C_, _lib.ptr(rng), site, p, _lib.stream_ptr()),
+            res_mode, _lib.ptr(out[PAD:]), 1, B, T, PAD, C_, _lib.ptr(rng), site, p, _lib.stream_ptr()),
             "eegx_bn_act_fwd_bf16")
         ctx.save_for_backward(ya, gamma_a, beta_a, yr if res_mode else None, gamma_r if res_mode == 2 else None,
                               beta_r if res_mode == 2 else None, mean_a, rstd_a, mean_r, rstd_r)
@@ -372,7 +372,7 @@ class _BnAct(torch.autograd.Function):
             _lib.ptr(dout[PAD:]), _lib.ptr(ya[PAD:]), _lib.ptr(mean_a), _lib.ptr(rstd_a), _lib.ptr(_f32(gamma_a)),
             _lib.ptr(_f32(beta_a)), _lib.ptr(yr[PAD:]) if res_mode else None, _lib.ptr(mean_r), _lib.ptr(rstd_r),
             _lib.ptr(gr), _lib.ptr(br), res_mode, int(training), _lib.ptr(da[PAD:]),
-            _lib.ptr(dr[PAD:]) if res_mode else None, _lib.ptr(sums), _lib.ptr(ws), ws.numel(), B, T, PAD, C_,
+            _lib.ptr(dr[PAD:]) if res_mode else None, _lib.ptr(sums), _lib.ptr(ws), ws.numel(), 1, B, T, PAD, C_,
             _lib.ptr(rng), site, p, _lib.stream_ptr()), "eegx_bn_act_bwd_bf16")
         targets = [(gamma_a, sums[1]), (beta_a, sums[0])] + ([(gamma_r, sums[2]), (beta_r, sums[0])] if res_mode == 2 else [])
         bufs = [grad_buffer(p_) for p_, _ in targets]
@@ -403,7 +403,7 @@ class _DwConv5(torch.autograd.Function):
         out = torch.empty_like(xg)
         w = _f32(weight).reshape(C_, 5)
         _lib.check(_lib.lib().eegx_dwconv5_fwd_bf16(_lib.ptr(xg[PAD:]), _lib.ptr(w), _lib.ptr(_f32(bias)),
-                                                    _lib.ptr(out[PAD:]), B, T, PAD, C_, _lib.stream_ptr()),
+                                                    _lib.ptr(out[PAD:]), 1, B, T, PAD, C_, _lib.stream_ptr()),
                    "eegx_dwconv5_fwd_bf16")
         ctx.save_for_backward(xg, weight, bias)
         ctx.cfg = (B, T)
@@ -421,7 +421,7 @@ class _DwConv5(torch.autograd.Function):
         ws = _workspace(lib.eegx_colreduce_workspace_bytes(C_), xg.device)
         w = _f32(weight).reshape(C_, 5)
         _lib.check(lib.eegx_dwconv5_bwd_bf16(_lib.ptr(dout[PAD:]), _lib.ptr(xg[PAD:]), _lib.ptr(w), _lib.ptr(dx[PAD:]),
-                                             _lib.ptr(dwdb), _lib.ptr(ws), ws.numel(), B, T, PAD, C_,
+                                             _lib.ptr(dwdb), _lib.ptr(ws), ws.numel(), 1, B, T, PAD, C_,
                                              _lib.stream_ptr()), "eegx_dwconv5_bwd_bf16")
         dw = dwdb[:5].t().reshape(weight.shape).to(weight.dtype)
         return dx, dw, dwdb[5].to(bias.dtype), None, None

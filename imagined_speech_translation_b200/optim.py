@@ -20,10 +20,42 @@ import torch
 from . import _lib, nn_ops
 
 
+class ParamStack:
+    """G same-shaped parameters (one per region encoder) that FlatAdamW has laid out back to back: ``p`` /
+    ``g`` are (G, *shape) fp32 views of the flat master / gradient buffers, ``w16`` the (G, *shape) bf16 shadow
+    the AdamW kernel keeps current.  The lock-step region path (``grouped.py``) reads its weights and
+    accumulates its weight gradients through these views -- one launch serves all G modules."""
+
+    def __init__(self, params, p, g, w16):
+        self.params, self.p, self.g, self._w16 = list(params), p, g, w16
+
+    def __len__(self):
+        return len(self.params)
+
+    def bound(self) -> bool:
+        """True while every parameter still is its slice of the stacked buffers."""
+        step = self.p.stride(0) * 4
+        base, gbase = self.p.data_ptr(), self.g.data_ptr()
+        return all(q.data_ptr() == base + i * step and q.grad is not None and q.grad.data_ptr() == gbase + i * step
+                   for i, q in enumerate(self.params))
+
+    def w16(self) -> torch.Tensor:
+        """The bf16 shadow, refreshed first if a parameter was modified in place since the last AdamW step."""
+        if any(getattr(q, "_eegx_w16_ver", -1) != q._version for q in self.params):
+            with torch.no_grad():
+                self._w16.copy_(self.p)
+            for q in self.params:
+                q._eegx_w16_ver = q._version
+        return self._w16
+
+
 class FlatAdamW(torch.optim.Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, stacks=None):
+        """stacks: optional list of parameter lists (e.g. ``BrainRegionEncoder.parameter_stacks()``): the members of
+        a list have one shape and are laid out back to back in the flat buffers, so that ``ParamStack`` views exist."""
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
+        self._stack_request = [list(st) for st in (stacks or []) if len(st) > 1]
         self._flat = None          # per group: dict(p, g, m, v, params)
         self._step = 0
         self._norm_sq = None
@@ -35,11 +67,28 @@ class FlatAdamW(torch.optim.Optimizer):
         """One contiguous fp32 gradient buffer for ALL groups (a single all-reduce covers it) and one
         parameter / moment buffer per group (the groups differ in learning rate)."""
         plan = []
+        live_stacks = []
         for group in self.param_groups:
             ps = [p for p in group['params'] if p.grad is not None]
             for p in ps:
                 if p.dtype != torch.float32 or not p.is_cuda:
                     raise _lib.EegxError("FlatAdamW needs float32 CUDA parameters (no CPU fallback)")
+            # members of a requested stack follow its first member (same shape, all in this group, all with gradients,
+            # 8-element multiples so that the stacked views are contiguous)
+            in_group = {id(p) for p in ps}
+            follow, skip = {}, set()
+            for st in self._stack_request:
+                if (all(id(q) in in_group for q in st) and len({tuple(q.shape) for q in st}) == 1
+                        and st[0].numel() % 8 == 0 and not any(id(q) in skip or id(q) in follow for q in st)):
+                    follow[id(st[0])] = st
+                    skip.update(id(q) for q in st[1:])
+                    live_stacks.append(st)
+            ordered = []
+            for p in ps:
+                if id(p) in skip:
+                    continue
+                ordered.extend(follow.get(id(p), [p]))
+            ps = ordered
             sizes = [(p.numel() + 7) // 8 * 8 for p in ps]          # every fp32 AND bf16-shadow view 16-byte aligned
             plan.append((ps, sizes))
         if not any(ps for ps, _ in plan):
@@ -65,12 +114,24 @@ class FlatAdamW(torch.optim.Optimizer):
                 p.data = flat_p[off:off + k].view_as(p)
                 p.grad = flat_g[off:off + k].view_as(p)
                 p._eegx_w16 = flat_w16[off:off + k].view_as(p)
+                p._eegx_w16_ver = p._version                  # flat_w16 is filled from flat_p right below
+                p._eegx_flat = (len(flats), off)               # (group index, offset inside the group's buffers)
                 off += n
             base += total
             flat_w16.copy_(flat_p)
             flats.append(dict(p=flat_p, g=flat_g, m=torch.zeros_like(flat_p), v=torch.zeros_like(flat_p),
                               w16=flat_w16, params=ps))
         self._flat = flats
+        self.stacks = []
+        for st in live_stacks:
+            gi, off = st[0]._eegx_flat
+            f, k, G = flats[gi], st[0].numel(), len(st)
+            shape = (G,) + tuple(st[0].shape)
+            stack = ParamStack(st, f['p'][off:off + G * k].view(shape), f['g'][off:off + G * k].view(shape),
+                               f['w16'][off:off + G * k].view(shape))
+            for i, q in enumerate(st):
+                q._eegx_stack = (stack, i)
+            self.stacks.append(stack)
         # parameters left outside (no gradient at build time) and the addresses the views must keep: step() checks both
         self._outside = [p for g in self.param_groups for p in g['params'] if id(p) not in self._offsets]
         self._expected_ptr = [(p, p.data_ptr(), p.grad.data_ptr()) for f in flats if f is not None for p in f['params']]

@@ -52,8 +52,10 @@ def get_optimizer_groups(model, config=CONFIG):
 
 def build_optimizer(model, config=CONFIG):
     """scripts/train.py:210-215: AdamW(eps 1e-8, betas .9/.999, weight_decay from the config)."""
+    enc = getattr(model, 'brain_encoder', None)
+    stacks = enc.parameter_stacks() if hasattr(enc, 'parameter_stacks') else None     # lock-step region path (grouped.py)
     return FlatAdamW(get_optimizer_groups(model, config), eps=1e-8, betas=(0.9, 0.999),
-                     weight_decay=config['weight_decay'])
+                     weight_decay=config['weight_decay'], stacks=stacks)
 
 
 def cosine_schedule_with_warmup(optimizer, num_warmup_steps, num_training_steps, num_cycles=0.5):
@@ -108,6 +110,7 @@ class EEGTrainer:
         # falls back to one all-reduce after backward)
         self.overlap_allreduce = os.environ.get('EEGX_OVERLAP_ALLREDUCE', '1') != '0'
         self._plan = None
+        self._plan_lock_step = None
         self._works = []
         self._grads_reduced = False
         self._graph_reduces = False
@@ -133,14 +136,30 @@ class EEGTrainer:
         encoders (attention stack -- split in two --, then CNN); a `fused.grad_boundary` sits at each of those transitions and
         its backward starts the all-reduce of the slice that has just become final.  Only what is left
         (region CNN stacks, tokens, positions: ~8 % of the bytes) is reduced after backward."""
-        if self._plan is not None:
-            return self._plan
         opt, model = self.optimizer, self.model
         enc, dec = model.brain_encoder, model.bart_decoder
+        from . import grouped
+        lock_step = getattr(enc, 'lock_step_regions', True) and grouped.available(list(enc.region_encoders.values()))
+        if self._plan is not None and self._plan_lock_step == lock_step:
+            return self._plan
+        self._plan_lock_step = lock_step
         plan = {('decoder', id(dec)): opt.grad_runs(list(dec.parameters())),
                 ('fusion', id(enc)): opt.grad_runs([p for n, p in enc.named_parameters()
                                                     if not n.startswith('region_encoders.')])}
-        for m in enc.region_encoders.values():
+        if lock_step:
+            # the regions run as one stacked pass: one boundary pair for all of them, and the stacked layout of the
+            # flat buffers makes the union of the regions' slices contiguous again
+            mods = list(enc.region_encoders.values())
+            mid = len(mods[0].attn_layers) // 2
+            upper = [p for m in mods for sub in (m.attn_layers[mid:], m.multi_scale_proj, m.projection, m.diversity_head)
+                     for p in sub.parameters()]
+            lower = [p for m in mods for sub in (m.attn_layers[:mid], m.cross_scale_attn) for p in sub.parameters()]
+            if mid > 0:
+                plan[('region_mid', 'group')] = opt.grad_runs(upper)
+                plan[('region', 'group')] = opt.grad_runs(lower)
+            else:
+                plan[('region', 'group')] = opt.grad_runs(upper + lower)
+        for m in ([] if lock_step else enc.region_encoders.values()):
             if getattr(m, 'cnn_only', False):
                 continue
             # two points per region: halfway through the attention stack (upper layers + heads) and at its input

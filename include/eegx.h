@@ -112,7 +112,7 @@ int eegx_dsp_forward(const eegx_dsp_plan* plan, const float* x, const int64_t* o
  * (main_model/src/models/layers.py:30-127, brain_encoder.py:31-92; SURVEY.md
  * section 2 "library-call sites that become sm_100a kernels").
  *
- *   D[b] (M x N) = alpha * A[b] (M x K) * B[b] (N x K)^T  (+ bias[N]) (+ GELU) (+ D[b])
+ *   D[g][b] (M x N) = alpha * A[g][b] (M x K) * B[g][b] (N x K)^T  (+ bias[g][N]) (+ GELU) (+ D[g][b])
  *
  * A, B: bf16.  a_mn_major = 0: A is stored M x K (K contiguous, leading dim lda);
  *              a_mn_major = 1: A is stored K x M (M contiguous).  Same for B / N.
@@ -138,6 +138,12 @@ typedef struct eegx_gemm_desc {
     int32_t force_block_n; /* 0 = auto (wave-quantisation cost model); 64 / 128 / 192 / 256 pins the N tile */
     float alpha;
     int32_t reserved;
+    /* Grouped launch (0 or 1 = off): `groups` independent problem sets in ONE launch -- the four region encoders,
+     * whose layers have identical shapes and their own weights (brain_encoder.py:148-150 runs them one after the
+     * other).  Problem (g, s), s < batch, reads A + g*stride_a_g + s*stride_a (same for B, D) and bias +
+     * g*stride_bias_g.  Group strides: multiples of 8 elements for A and B. */
+    int64_t groups;
+    int64_t stride_a_g, stride_b_g, stride_d_g, stride_bias_g;
 } eegx_gemm_desc;
 
 int eegx_gemm_bf16(const eegx_gemm_desc* desc, const void* A, const void* B, const float* bias,
@@ -179,19 +185,35 @@ int eegx_adamw_clip_f32(float* p, const float* g, float* m, float* v, int64_t n,
  * (M = B*(T+2*pad)) x C matrix whose other rows are zero, with `pad` more zero rows before
  * m = 0 and after m = M-1, so nn.Conv1d is a GEMM over overlapping rows.  Pointers address row
  * m = 0; "out" buffers of this kind have every row (guards included) written.
+ *
+ * Parameter groups (G / groups): the four region encoders of BrainRegionEncoder have layers of identical
+ * shape with their own parameters (brain_encoder.py:148-150 runs them one after the other).  Entry points
+ * that read parameters take G: the activation then holds G equal blocks of rows (G * B trials in ONE guarded
+ * buffer), block g uses parameter set g (gamma / beta / weights / statistics stacked (G, ...), stride given or
+ * C), and parameter gradients come out per group.  G = 1 is a single module.
  * ------------------------------------------------------------------------ */
 
 /* nn.LayerNorm(C) (+ nn.GELU if act = 1) (+ nn.Dropout) on (rows, C) bf16
  * (main_model/src/models/layers.py:61-71, 84-127, 232, 240).  mean / rstd: (rows) fp32 saved for backward. */
+/* groups > 1: rows split evenly; gamma / beta (and dgamma / dbeta) of group g at + g * param_stride elements. */
 int eegx_layernorm_fwd_bf16(const void* x, const float* gamma, const float* beta, void* y, float* mean,
-                            float* rstd, int64_t rows, int64_t C, float eps, int act, const uint64_t* rng_state,
-                            uint32_t site, float p, void* stream);
+                            float* rstd, int64_t rows, int64_t C, int64_t groups, int64_t param_stride, float eps,
+                            int act, const uint64_t* rng_state, uint32_t site, float p, void* stream);
 size_t eegx_layernorm_bwd_workspace_bytes(int64_t C);
 /* accumulate != 0: dgamma / dbeta += (they may point straight into the parameters' gradient buffers). */
 int eegx_layernorm_bwd_bf16(const void* dy, const void* x, const float* gamma, const float* beta,
                             const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
                             int accumulate, void* workspace, size_t workspace_bytes, int64_t rows, int64_t C,
-                            int act, const uint64_t* rng_state, uint32_t site, float p, void* stream);
+                            int64_t groups, int64_t param_stride, int act, const uint64_t* rng_state, uint32_t site,
+                            float p, void* stream);
+/* Token assembly in front of the attention stack (layers.py:214-225), G groups of B sequences:
+ * out[gb, s, :] = (s == 0 ? cls[g] : s < 4 ? temporal[g][s-1] : h[gb, s-4]) + pos[g][s]; h (G*B*T, d), out
+ * (G*B*(T+4), d) bf16; cls (d), temporal (3, d), pos (T+4, d) fp32 per group at the given strides.
+ * Backward: dh[gb, t] = dout[gb, t+4]; d(pos) is eegx_colsum_bf16 of dout viewed (G, B, (T+4)*d). */
+int eegx_assemble_tokens_fwd_bf16(const void* h, const float* cls, int64_t cls_gstride, const float* temporal,
+                                  int64_t temporal_gstride, const float* pos, int64_t pos_gstride, void* out, int64_t G,
+                                  int64_t B, int64_t T, int64_t d, void* stream);
+int eegx_assemble_tokens_bwd_bf16(const void* dout, void* dh, int64_t GB, int64_t T, int64_t d, void* stream);
 
 /* out = a + scale * dropout(b): the residual adds of layers.py:234, 242, 251 / brain_encoder.py:165. */
 int eegx_add_dropout_fwd_bf16(const void* a, const void* b, void* out, int64_t n, float scale,
@@ -214,40 +236,45 @@ int eegx_glu_bwd_bf16(const void* dout, const void* ag, void* dag, int64_t rows,
  * mean / rstd (C) fp32; running_mean / running_var updated in place with `momentum` (unbiased
  * variance) unless NULL.  Two fixed-order stages (bit-stable). */
 size_t eegx_colreduce_workspace_bytes(int64_t C);
-/* out[c] (+)= sum_r y[r * ld + c] of a (rows, C) bf16 matrix with row pitch ld, fp32, fixed order: the bias
- * gradients of nn.Linear / nn.Conv1d (accumulate != 0: added into the gradient buffer). */
-int eegx_colsum_bf16(const void* y, int64_t ld, int64_t rows, int64_t C, float* out, int accumulate, void* workspace,
-                     size_t workspace_bytes, void* stream);
-/* dst[i] (+)= sum_s part[s * n + i]: folds the split-K partials of a weight-gradient GEMM into the gradient. */
-int eegx_accumulate_partials_f32(const float* part, int64_t s, int64_t n, float* dst, int accumulate, void* stream);
+/* out[g][c] (+)= sum_r y[g * y_gstride + r * ld + c] of G (rows, C) bf16 matrices with row pitch ld, fp32, fixed
+ * order: the bias gradients of nn.Linear / nn.Conv1d (accumulate != 0: added into the gradient buffer); out of
+ * group g at + g * out_gstride. */
+int eegx_colsum_bf16(const void* y, int64_t ld, int64_t G, int64_t y_gstride, int64_t rows, int64_t C, float* out,
+                     int64_t out_gstride, int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+/* dst[g * dst_gstride + i] (+)= sum_s part[(s * G + g) * n + i]: folds the split-K partials of G weight-gradient
+ * GEMMs into their gradients (G = 1: dst contiguous). */
+int eegx_accumulate_partials_f32(const float* part, int64_t s, int64_t G, int64_t n, float* dst, int64_t dst_gstride,
+                                 int accumulate, void* stream);
 /* nn.Conv1d weight gradient: part is s partials of the GEMM layout (Cout, k * Cin) [index tap * Cin + ci];
  * dst, laid out like the parameter (Cout, Cin, k), (+)= their sum. */
 int eegx_accumulate_conv_wgrad_f32(const float* part, int64_t s, int64_t Cout, int64_t Cin, int64_t k, float* dst,
                                    int accumulate, void* stream);
-int eegx_bn_stats_bf16(const void* y, int64_t B, int64_t T, int64_t pad, int64_t C, float eps, float* mean,
-                       float* rstd, float* running_mean, float* running_var, float momentum, void* workspace,
-                       size_t workspace_bytes, void* stream);
+/* G groups of B trials: mean / rstd (G, C); running statistics of group g at + g * running_gstride. */
+int eegx_bn_stats_bf16(const void* y, int64_t G, int64_t B, int64_t T, int64_t pad, int64_t C, float eps, float* mean,
+                       float* rstd, float* running_mean, float* running_var, int64_t running_gstride, float momentum,
+                       void* workspace, size_t workspace_bytes, void* stream);
 /* out = zero_pad_rows( dropout( gelu( bn_a(ya) + residual ) ) )  (layers.py:142-174)
  * res_mode 0: none; 1: identity residual yr; 2: bn_r(yr) (the 1x1-conv + BatchNorm residual). */
 int eegx_bn_act_fwd_bf16(const void* ya, const float* mean_a, const float* rstd_a, const float* gamma_a,
                          const float* beta_a, const void* yr, const float* mean_r, const float* rstd_r,
-                         const float* gamma_r, const float* beta_r, int res_mode, void* out, int64_t B, int64_t T,
-                         int64_t pad, int64_t C, const uint64_t* rng_state, uint32_t site, float p, void* stream);
-/* Backward of the above.  sums (3, C) fp32: [0] dbeta (both sides), [1] dgamma_a, [2] dgamma_r.
+                         const float* gamma_r, const float* beta_r, int res_mode, void* out, int64_t G, int64_t B,
+                         int64_t T, int64_t pad, int64_t C, const uint64_t* rng_state, uint32_t site, float p, void* stream);
+/* Backward of the above.  sums (G, 3, C) fp32: [0] dbeta (both sides), [1] dgamma_a, [2] dgamma_r.  Statistics and
+ * affine vectors are (G, C).
  * da / dr: gradients w.r.t. ya / yr as guarded rows.  train = 0: statistics are constants (eval). */
 int eegx_bn_act_bwd_bf16(const void* dout, const void* ya, const float* mean_a, const float* rstd_a,
                          const float* gamma_a, const float* beta_a, const void* yr, const float* mean_r,
                          const float* rstd_r, const float* gamma_r, const float* beta_r, int res_mode, int train,
-                         void* da, void* dr, float* sums, void* workspace, size_t workspace_bytes, int64_t B,
+                         void* da, void* dr, float* sums, void* workspace, size_t workspace_bytes, int64_t G, int64_t B,
                          int64_t T, int64_t pad, int64_t C, const uint64_t* rng_state, uint32_t site, float p,
                          void* stream);
-/* Depthwise Conv1d k = 5, groups = C (layers.py:157) on guarded rows; w (C, 5), bias (C) fp32.
- * Backward: dx guarded rows; dwdb (6, C) fp32 = [dw tap 0..4, dbias]. */
-int eegx_dwconv5_fwd_bf16(const void* x, const float* w, const float* bias, void* out, int64_t B, int64_t T,
+/* Depthwise Conv1d k = 5, groups = C (layers.py:157) on guarded rows; w (G, C, 5), bias (G, C) fp32.
+ * Backward: dx guarded rows; dwdb (G, 6, C) fp32 = [dw tap 0..4, dbias]. */
+int eegx_dwconv5_fwd_bf16(const void* x, const float* w, const float* bias, void* out, int64_t G, int64_t B, int64_t T,
                           int64_t pad, int64_t C, void* stream);
 int eegx_dwconv5_bwd_bf16(const void* dout, const void* x, const float* w, void* dx, float* dwdb,
-                          void* workspace, size_t workspace_bytes, int64_t B, int64_t T, int64_t pad, int64_t C,
-                          void* stream);
+                          void* workspace, size_t workspace_bytes, int64_t G, int64_t B, int64_t T, int64_t pad,
+                          int64_t C, void* stream);
 /* SqueezeExciteBlock (layers.py:288-298): s = mean_t x (B, C) fp32; out = dropout(x * e[b, c]) written as
  * compact (B*T, C) rows; backward: dx (valid guarded rows) and de (B, C). */
 int eegx_group_mean_bf16(const void* x, float* s, int64_t B, int64_t T, int64_t pad, int64_t C, void* stream);

@@ -97,3 +97,48 @@ def test_gemm_rejects_bad_arguments():
     from imagined_speech_translation_b200 import EegxError
     with pytest.raises(EegxError):
         ops.gemm(_mk((128, 70), 1)[:, :64], b)      # lda = 70: not a multiple of 8
+
+
+def test_gemm_grouped_forward_with_per_group_bias():
+    """G problem sets in one launch (the four region encoders' identical layers): own weights, own bias."""
+    G, M, K, N = 4, 592, 768, 384
+    x, w = _mk((G, M, K), 20), _mk((G, N, K), 21)
+    bias = torch.randn(G, N, device="cuda")
+    y = ops.gemm(x, w, bias, grouped=True, out_dtype=torch.float32)
+    ref = torch.bmm(x.float(), w.float().transpose(1, 2)) + bias[:, None, :]
+    assert y.shape == (G, M, N) and _rel(y, ref) <= 1e-4
+    yg = ops.gemm(x, w, bias, grouped=True, gelu=True)                       # bf16 out, GELU epilogue
+    assert _rel(yg.float(), torch.nn.functional.gelu(ref)) <= 2 ** -7
+    dx = ops.gemm(y.to(torch.bfloat16), w, b_mn_major=True, grouped=True, out_dtype=torch.float32)
+    assert _rel(dx, torch.bmm(y.to(torch.bfloat16).float(), w.float())) <= 1e-4
+
+
+@pytest.mark.parametrize("S", [1, 2, 4])
+def test_gemm_grouped_split_k_weight_gradient(S):
+    """(G, S) problems: the weight gradient of G layers with the reduction split into S chunks; partials land in
+    an (S, G, N, K) buffer (strided `out` view) and accumulate into a (G, N, K) gradient buffer when S = 1."""
+    G, R, N, K = 4, 1024, 256, 192
+    dy, x = _mk((G, R, N), 22), _mk((G, R, K), 23)
+    ref = torch.bmm(dy.float().transpose(1, 2), x.float())                  # (G, N, K)
+    dy4 = dy.view(G, S, R // S, N)
+    x4 = x.view(G, S, R // S, K)
+    part = torch.empty(S, G, N, K, device="cuda")
+    out = ops.gemm(dy4, x4, a_mn_major=True, b_mn_major=True, out=part.permute(1, 0, 2, 3))
+    assert out.data_ptr() == part.data_ptr()
+    assert _rel(part.sum(0), ref) <= 1e-4
+    if S == 1:
+        acc = ref.clone()
+        ops.gemm(dy, x, a_mn_major=True, b_mn_major=True, grouped=True, out=acc, accumulate=True)
+        assert _rel(acc, 2 * ref) <= 1e-4
+
+
+def test_gemm_grouped_overlapping_rows_conv():
+    """Grouped implicit-im2col: group stride = rows * C_in of ONE guarded buffer holding the G region activations."""
+    G, M, Cin, k, Cout = 4, 328, 128, 7, 256
+    buf = _mk((G * M + 8, Cin), 24)
+    w = _mk((G, Cout, k * Cin), 25)
+    a = buf.as_strided((G, M, k * Cin), (M * Cin, Cin, 1), (4 - k // 2) * Cin)
+    y = ops.gemm(a, w, grouped=True, out_dtype=torch.float32)
+    for g in range(G):
+        rows = torch.stack([buf[4 - k // 2 + g * M + m: 4 - k // 2 + g * M + m + k].reshape(-1) for m in range(M)])
+        assert _rel(y[g], rows.float() @ w[g].float().t()) <= 1e-4
