@@ -35,8 +35,13 @@ constexpr int CR_COLS = 64;
 
 // ---- column reduction skeleton: each lane owns 2 columns, warps stride over the rows of the
 // CTA's slab, then the 8 warps are summed in order and the CTA partial is written.
-template <int NACC, typename F>
-__device__ __forceinline__ void col_reduce(const RowGeom& g, int C, float* __restrict__ part, F f) {
+struct NoPrep {
+    __device__ __forceinline__ void operator()(int, int) const {}
+};
+
+// prep(c, grp) runs once per thread before the row loop (loop-invariant per-column parameters into registers)
+template <int NACC, typename F, typename P = NoPrep>
+__device__ __forceinline__ void col_reduce(const RowGeom& g, int C, float* __restrict__ part, F f, P prep = P()) {
     __shared__ float red[CR_THREADS / 32][NACC][CR_COLS];
     constexpr int NW = CR_THREADS / 32;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -52,6 +57,7 @@ __device__ __forceinline__ void col_reduce(const RowGeom& g, int C, float* __res
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k][0] = acc[k][1] = 0.0f;
     if (c < C && m0 + wid < m1) {
+        prep(c, grp);
         // the position inside the trial is tracked incrementally (no 64-bit modulo per row)
         long long m = m0 + wid;
         int r = (int)(m % g.Tp);
@@ -190,48 +196,44 @@ bn_act_fwd_kernel(BnSide a, BnSide r, int res_mode, __nv_bfloat16* __restrict__ 
     }
 }
 
-// dpre = dout * dropout_mask * gelu'(pre), pre = bn(a) + residual; shared by the two backward passes
-__device__ __forceinline__ void bn_act_dpre(const BnSide& a, const BnSide& r, int res_mode,
-                                            const __nv_bfloat16* dout, long long m, int c, int C, int po,
-                                            const DropoutGen& gen, float (&dp)[2], float (&ha)[2], float (&hr)[2]) {
-    // po: offset of this row's parameter group in the (G, C) statistics / affine vectors
-    const float2 va = ld2(a.x + m * C + c);
-    const float2 d = ld2(dout + m * C + c);
-    const int pc = po + c;
-    ha[0] = (va.x - a.mean[pc]) * a.rstd[pc];
-    ha[1] = (va.y - a.mean[pc + 1]) * a.rstd[pc + 1];
-    float pre0 = fmaf(ha[0], a.gamma[pc], a.beta[pc]), pre1 = fmaf(ha[1], a.gamma[pc + 1], a.beta[pc + 1]);
-    hr[0] = hr[1] = 0.0f;
-    if (res_mode == 1) {
-        const float2 vr = ld2(r.x + m * C + c);
-        pre0 += vr.x; pre1 += vr.y;
-    } else if (res_mode == 2) {
-        const float2 vr = ld2(r.x + m * C + c);
-        hr[0] = (vr.x - r.mean[pc]) * r.rstd[pc];
-        hr[1] = (vr.y - r.mean[pc + 1]) * r.rstd[pc + 1];
-        pre0 += fmaf(hr[0], r.gamma[pc], r.beta[pc]);
-        pre1 += fmaf(hr[1], r.gamma[pc + 1], r.beta[pc + 1]);
-    }
-    float m0, m1;
-    gen.mask_pair((unsigned long long)(m * C + c) >> 3, c & 7, m0, m1);
-    dp[0] = d.x * m0 * gelu_grad_f(pre0);
-    dp[1] = d.y * m1 * gelu_grad_f(pre1);
-}
-
-// partial sums per channel: [0] sum dpre, [1] sum dpre * xhat_a, [2] sum dpre * xhat_r
+// partial sums per channel: [0] sum dpre, [1] sum dpre * xhat_a, [2] sum dpre * xhat_r; dpre itself (the erf / exp /
+// Philox work of this pass) is kept as bf16 in `dpre_out` so that the apply pass does not recompute it.  The
+// per-column statistics and affine parameters are loop invariants held in registers.
 __global__ void __launch_bounds__(CR_THREADS)
 bn_act_bwd_reduce_kernel(BnSide a, BnSide r, int res_mode, const __nv_bfloat16* __restrict__ dout, RowGeom g, int C,
-                         DropoutCfg dc, float* __restrict__ part) {
+                         DropoutCfg dc, float* __restrict__ part, __nv_bfloat16* __restrict__ dpre_out) {
     EEGX_PDL_SYNC();
     const DropoutGen gen(dc);
-    col_reduce<3>(g, C, part, [&](long long m, int c, int grp, float (&acc)[3][2]) {
-        float dp[2], ha[2], hr[2];
-        bn_act_dpre(a, r, res_mode, dout, m, c, C, grp * C, gen, dp, ha, hr);
+    float mu_a[2], rs_a[2], ga_a[2], be_a[2], mu_r[2] = {0.f, 0.f}, rs_r[2] = {0.f, 0.f}, ga_r[2] = {0.f, 0.f}, be_r[2] = {0.f, 0.f};
+    col_reduce<3>(g, C, part, [&](long long m, int c, int, float (&acc)[3][2]) {
+        const float2 va = ld2(a.x + m * C + c);
+        const float2 d = ld2(dout + m * C + c);
+        const float ha0 = (va.x - mu_a[0]) * rs_a[0], ha1 = (va.y - mu_a[1]) * rs_a[1];
+        float pre0 = fmaf(ha0, ga_a[0], be_a[0]), pre1 = fmaf(ha1, ga_a[1], be_a[1]);
+        float hr0 = 0.0f, hr1 = 0.0f;
+        if (res_mode == 1) {
+            const float2 vr = ld2(r.x + m * C + c);
+            pre0 += vr.x; pre1 += vr.y;
+        } else if (res_mode == 2) {
+            const float2 vr = ld2(r.x + m * C + c);
+            hr0 = (vr.x - mu_r[0]) * rs_r[0]; hr1 = (vr.y - mu_r[1]) * rs_r[1];
+            pre0 += fmaf(hr0, ga_r[0], be_r[0]); pre1 += fmaf(hr1, ga_r[1], be_r[1]);
+        }
+        float m0, m1;
+        gen.mask_pair((unsigned long long)(m * C + c) >> 3, c & 7, m0, m1);
+        const float dp0 = d.x * m0 * gelu_grad_f(pre0), dp1 = d.y * m1 * gelu_grad_f(pre1);
+        *reinterpret_cast<__nv_bfloat162*>(dpre_out + m * C + c) = __floats2bfloat162_rn(dp0, dp1);
+        acc[0][0] += dp0; acc[0][1] += dp1;
+        acc[1][0] = fmaf(dp0, ha0, acc[1][0]); acc[1][1] = fmaf(dp1, ha1, acc[1][1]);
+        acc[2][0] = fmaf(dp0, hr0, acc[2][0]); acc[2][1] = fmaf(dp1, hr1, acc[2][1]);
+    }, [&](int c, int grp) {
+        const int pc = grp * C + c;
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            acc[0][e] += dp[e];
-            acc[1][e] = fmaf(dp[e], ha[e], acc[1][e]);
-            acc[2][e] = fmaf(dp[e], hr[e], acc[2][e]);
+            mu_a[e] = a.mean[pc + e]; rs_a[e] = a.rstd[pc + e]; ga_a[e] = a.gamma[pc + e]; be_a[e] = a.beta[pc + e];
+            if (res_mode == 2) {
+                mu_r[e] = r.mean[pc + e]; rs_r[e] = r.rstd[pc + e]; ga_r[e] = r.gamma[pc + e]; be_r[e] = r.beta[pc + e];
+            }
         }
     });
 }
@@ -252,10 +254,21 @@ bn_act_bwd_apply_kernel(BnSide a, BnSide r, int res_mode, const __nv_bfloat16* _
         const int c = (int)(i % c2) * 2;
         float oa[2] = {0.0f, 0.0f}, orr[2] = {0.0f, 0.0f};
         if (m >= 0 && m < g.M && g.valid(m)) {
-            float dp[2], ha[2], hr[2];
+            float dp[2], ha[2], hr[2] = {0.0f, 0.0f};
             const int grp = (int)(m / g.Mg), po = grp * C;
             const float* sg = sums + (long long)grp * 3 * C;       // sums: (G, 3, C)
-            bn_act_dpre(a, r, res_mode, dout, m, c, C, po, gen, dp, ha, hr);
+            {   // dpre was left in `da` by the reduce pass (same element: read here, overwritten below)
+                const float2 dpv = ld2(da + m * C + c);
+                dp[0] = dpv.x; dp[1] = dpv.y;
+                const float2 va = ld2(a.x + m * C + c);
+                ha[0] = (va.x - a.mean[po + c]) * a.rstd[po + c];
+                ha[1] = (va.y - a.mean[po + c + 1]) * a.rstd[po + c + 1];
+                if (res_mode == 2) {
+                    const float2 vr = ld2(r.x + m * C + c);
+                    hr[0] = (vr.x - r.mean[po + c]) * r.rstd[po + c];
+                    hr[1] = (vr.y - r.mean[po + c + 1]) * r.rstd[po + c + 1];
+                }
+            }
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const float s1 = train ? sg[c + e] * inv_n : 0.0f;
@@ -730,7 +743,7 @@ int eegx_bn_act_bwd_bf16(const void* dout, const void* ya, const float* mean_a, 
     float* part = static_cast<float*>(workspace);
     dim3 grid((unsigned)((C + CR_COLS - 1) / CR_COLS), (unsigned)(slabs * G));
     eegx::launch(bn_act_bwd_reduce_kernel, grid, CR_THREADS, 0, st, a, r, res_mode, static_cast<const __nv_bfloat16*>(dout), g,
-                                                          (int)C, dc, part);
+                                                          (int)C, dc, part, static_cast<__nv_bfloat16*>(da));
     eegx::launch(sum_partials_kernel, dim3((unsigned)((C + 31) / 32), 3, (unsigned)G), 256, 0, st, part, slabs, 3, (int)C, sums,
                  (long long)(3 * C), 0);
     eegx::launch(bn_act_bwd_apply_kernel, ew_grid((g.M + 2 * pad) * (C / 2)), 256, 0, st, 

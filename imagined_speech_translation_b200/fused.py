@@ -88,6 +88,53 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     return t
 
 
+# ------------------------------------------------------------------------------------------ deferred weight gradients
+# Nothing on the critical path of backward waits for a weight / bias gradient: the data gradient of a layer feeds the
+# next backward node, its parameter gradients only have to exist when backward ends.  The latency-bound stretches of
+# backward (decoder: M = 4096 rows, fusion stage and heads: M <= 1024) leave most SMs idle, so the in-place
+# weight-gradient work is issued on a side stream where it fills them; the stream is joined when backward ends (a
+# final callback of the autograd engine) and at every gradient-ready boundary of the all-reduce overlap.
+import os as _os
+
+DEFER_WGRAD = _os.environ.get("EEGX_DEFER_WGRAD", "1") != "0"
+_side_streams: dict = {}
+_deferred_pending = [False]
+
+
+def deferred(fn, *tensors) -> None:
+    """Run fn() -- work that only ACCUMULATES parameter gradients in place -- on the side stream.  `tensors`: every
+    tensor of the current stream that fn reads (kept alive for the side stream by the caching allocator)."""
+    t0 = next((t for t in tensors if t is not None), None)
+    if not DEFER_WGRAD or t0 is None or not t0.is_cuda:
+        fn()
+        return
+    dev = t0.device
+    cur = torch.cuda.current_stream(dev)
+    side = _side_streams.get(dev.index)
+    if side is None:
+        side = _side_streams[dev.index] = torch.cuda.Stream(device=dev)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        fn()
+    for t in tensors:
+        if t is not None:
+            t.record_stream(side)
+    if not _deferred_pending[0]:
+        _deferred_pending[0] = True
+        torch.autograd.Variable._execution_engine.queue_callback(_join_at_end_of_backward)
+
+
+def join_side() -> None:
+    """The current stream waits for everything deferred so far (gradients complete from its point of view)."""
+    for idx, side in _side_streams.items():
+        torch.cuda.current_stream(idx).wait_stream(side)
+
+
+def _join_at_end_of_backward() -> None:
+    _deferred_pending[0] = False
+    join_side()
+
+
 def _f32(p: torch.Tensor) -> torch.Tensor:
     p = p.detach()
     return p if p.dtype == torch.float32 and p.is_contiguous() else p.float().contiguous()

@@ -171,9 +171,12 @@ class _GLinear(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = ops.gemm(dy3, lw.w16(), b_mn_major=True, grouped=True).view(G * M, K)
-        gwgrad(dy3, x.view(G, M, K), lw.wg())
-        if lw.bst is not None:
-            gcolsum(dy3, lw.bg())
+
+        def grads():
+            gwgrad(dy3, x.view(G, M, K), lw.wg())
+            if lw.bst is not None:
+                gcolsum(dy3, lw.bg())
+        fused.deferred(grads, dy, x)
         return dx, None, None, None
 
 
@@ -202,13 +205,15 @@ class _GLinearCat(torch.autograd.Function):
         dy = dy.contiguous()
         dy3 = dy.view(G, M, dy.shape[1])
         dx = ops.gemm(dy3, _cat_pack(lws), b_mn_major=True, grouped=True).view(G * M, K) if ctx.needs_input_grad[0] else None
-        x3, off = x.view(G, M, K), 0
-        for lw in lws:
-            n = lw.wst.p.shape[1]
-            sl = dy3[:, :, off:off + n]
-            gwgrad(sl, x3, lw.wg())
-            gcolsum(sl, lw.bg())
-            off += n
+        def grads():
+            x3, off = x.view(G, M, K), 0
+            for lw in lws:
+                n = lw.wst.p.shape[1]
+                sl = dy3[:, :, off:off + n]
+                gwgrad(sl, x3, lw.wg())
+                gcolsum(sl, lw.bg())
+                off += n
+        fused.deferred(grads, dy, x)
         return dx, None, None, None
 
 
@@ -481,18 +486,21 @@ class _GConv(torch.autograd.Function):
         dyg = dyg.contiguous()                       # clean guarded tensor: zero outside the valid rows
         dy3 = dyg[PAD:PAD + G * Mg].view(G, Mg, Cout)
         a_view = xg.as_strided((G, Mg, k * Cin), (Mg * Cin, Cin, 1), xg.storage_offset() + (PAD - p) * Cin)
-        part = _wgrad_partials(dy3, a_view)                                                  # (s, G, Cout, k*Cin)
-        _lib.check(_lib.lib().eegx_accumulate_conv_wgrad_f32(_lib.ptr(part), part.shape[0], G * Cout, Cin, k,
-                                                             _lib.ptr(wst.g), 1, _lib.stream_ptr()),
-                   "eegx_accumulate_conv_wgrad_f32")
+
+        def grads():
+            part = _wgrad_partials(dy3, a_view)                                              # (s, G, Cout, k*Cin)
+            _lib.check(_lib.lib().eegx_accumulate_conv_wgrad_f32(_lib.ptr(part), part.shape[0], G * Cout, Cin, k,
+                                                                 _lib.ptr(wst.g), 1, _lib.stream_ptr()),
+                       "eegx_accumulate_conv_wgrad_f32")
+            if bst is not None and bias_grad:        # a bias in front of a train-mode BatchNorm has a zero gradient
+                gcolsum(dy3, bst.g)
+        fused.deferred(grads, dyg, xg)
         dxg = None
         if ctx.needs_input_grad[0]:
             a = dyg.as_strided((G, Mg, k * Cout), (Mg * Cout, Cout, 1), dyg.storage_offset() + (PAD - p) * Cout)
             dxg = torch.empty(G * Mg + 2 * PAD, Cin, dtype=torch.bfloat16, device=dyg.device)
             # guard rows stay unwritten: every consumer reads rows [0, G*Mg) only and masks the padding rows
             ops.gemm(a, _conv_dgrad_pack(wst), b_mn_major=True, grouped=True, out=dxg[PAD:PAD + G * Mg].view(G, Mg, Cin))
-        if bst is not None and bias_grad:            # a bias in front of a train-mode BatchNorm has a zero gradient
-            gcolsum(dy3, bst.g)
         return dxg, None, None, None, None, None, None
 
 

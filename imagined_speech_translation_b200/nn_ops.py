@@ -149,12 +149,21 @@ class _Linear(torch.autograd.Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = ops.gemm(dy, w16, b_mn_major=True)                                   # (M,N) @ (N,K)
+        into = _grad2d(weight) if ctx.n_pad == 0 and ctx.needs_input_grad[1] else None
+        gb = fused.grad_buffer(ctx.bias_ref) if ctx.n_pad == 0 and ctx.has_bias and ctx.needs_input_grad[2] else None
+        want_b = ctx.has_bias and ctx.needs_input_grad[2]
+        if into is not None and (gb is not None or not want_b):
+            # both parameter gradients accumulate in place: off the critical path (fused.deferred)
+            def grads():
+                _wgrad(dy, x, into)
+                if gb is not None:
+                    fused.colsum(dy, gb)
+            fused.deferred(grads, dy, x)
+            return dx, None, None, None
         if ctx.needs_input_grad[1]:
-            into = _grad2d(weight) if ctx.n_pad == 0 else None
             dw = _wgrad(dy, x, into)                                                     # dy^T @ x
             dw = dw[:N] if dw is not None else None
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = fused.grad_buffer(ctx.bias_ref) if ctx.n_pad == 0 else None
+        if want_b:
             db = fused.colsum(dy, gb)
             db = db[:N] if db is not None else None
         return dx, dw, db, None
@@ -258,6 +267,17 @@ class _LinearCat(torch.autograd.Function):
         bs = ctx.biases
         dy = dy.contiguous()
         dx = ops.gemm(dy, _w_cat(ws), b_mn_major=True) if ctx.needs_input_grad[0] else None
+        if all(_grad2d(w) is not None for w in ws) and all(fused.grad_buffer(b) is not None for b in bs):
+            def grads():
+                off = 0
+                for w, b in zip(ws, bs):
+                    n = w.shape[0]
+                    sl = dy[:, off:off + n]
+                    _wgrad(sl, x, _grad2d(w))
+                    fused.colsum(sl, fused.grad_buffer(b))
+                    off += n
+            fused.deferred(grads, dy, x)
+            return (dx, *([None] * (2 * len(ws))))
         dws, dbs, off = [], [], 0
         for w, b in zip(ws, bs):
             n = w.shape[0]

@@ -199,6 +199,7 @@ class EEGTrainer:
     def _on_boundary(self, key):
         runs = self._overlap_plan().get(key)
         if runs:
+            fused.join_side()          # weight gradients deferred to the side stream belong to the slice as well
             self._reduce_runs(runs)
 
     def _optimizer_step(self, step_scheduler: bool):

@@ -65,8 +65,8 @@ def test_flat_adamw_state_dict_interchanges_with_torch_adamw():
     sd = oa.state_dict()
     assert set(sd['state']) == set(ob.state_dict()['state'])              # the unused layer has no entry in either
     for k, st in ob.state_dict()['state'].items():
-        torch.testing.assert_close(sd['state'][k]['exp_avg'], st['exp_avg'], rtol=1e-5, atol=1e-6)
-        torch.testing.assert_close(sd['state'][k]['exp_avg_sq'], st['exp_avg_sq'], rtol=1e-5, atol=1e-9)
+        torch.testing.assert_close(sd['state'][k]['exp_avg'], st['exp_avg'], rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(sd['state'][k]['exp_avg_sq'], st['exp_avg_sq'], rtol=1e-4, atol=1e-7)
         assert float(sd['state'][k]['step']) == float(st['step']) == 3.0
     # ours -> torch
     c = _toy(5)

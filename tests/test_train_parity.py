@@ -142,8 +142,10 @@ def test_three_optimizer_steps_match_the_reference_trainer(tag):
     # resolution of the terms it is a difference of get a noise-driven DIRECTION here: norms and directions are
     # compared where the gradient is resolved (>= 1e-2 of the largest) in every step.
     top = [max(g.values()) for g in gold["param_grad_norm"]]
+    # (in_proj_bias is left out: its key third has an identically zero gradient -- softmax is shift invariant -- so
+    # a third of that vector moves by Adam-normalised round-off in the reference whatever the rest does)
     live = [n for n in gold["param_grad_norm"][-1]
-            if all(g[n] > 1e-2 * t for g, t in zip(gold["param_grad_norm"], top))]
+            if all(g[n] > 1e-2 * t for g, t in zip(gold["param_grad_norm"], top)) and not n.endswith("in_proj_bias")]
     now = dict(model.named_parameters())
     ratios, cosines = [], {}
     for n, p in now.items():
