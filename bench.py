@@ -36,13 +36,35 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 
+# BASELINE.json configs[2] ("stft", the configuration the metric is quoted on) and configs[3] ("long")
+WORKLOADS = {
+    "stft": {"B": 256, "C": 64, "T": 2048, "n_fft": 256, "hop": 64, "per_region": 16,
+             "title": "BASELINE configs[2]", "shape": "64 ch x 2048 samples, FIR 65 taps, STFT n_fft=256 hop=64"},
+    "long": {"B": 256, "C": 128, "T": 4096, "n_fft": 1024, "hop": 256, "per_region": 32,
+             "title": "BASELINE configs[3]",
+             "shape": "high-density 128 ch x 4096 samples, FIR 65 taps, long-window STFT n_fft=1024 hop=256"},
+}
 B_PER_GPU, C, T = 256, 64, 2048
 N_FFT, HOP = 256, 64
 F, NF = N_FFT // 2 + 1, 1 + T // HOP
 L_TOK = 16
 COUNTS = {"frontal": 16, "temporal": 16, "central": 16, "parietal": 16}
-DSP_BYTES_PER_TRIAL = 4 * C * T + 4 * C * F * NF          # 1,614,080
-CPU_SAMPLE_B = 4
+DSP_BYTES_PER_TRIAL = 4 * C * T + 4 * C * F * NF          # 1,614,080; 6,562,304 for configs[3]
+CONFIG_NAME = "stft"
+CPU_SAMPLE_B = 32                                          # BASELINE configs[0]: batch 32 on the host cores
+
+
+def select_config(name):
+    """Set the module-level shape constants for the chosen BASELINE configuration."""
+    global B_PER_GPU, C, T, N_FFT, HOP, F, NF, COUNTS, DSP_BYTES_PER_TRIAL, CONFIG_NAME
+    w = WORKLOADS[name]
+    CONFIG_NAME = name
+    B_PER_GPU, C, T, N_FFT, HOP = w["B"], w["C"], w["T"], w["n_fft"], w["hop"]
+    F, NF = N_FFT // 2 + 1, 1 + T // HOP
+    COUNTS = {k: w["per_region"] for k in ("frontal", "temporal", "central", "parietal")}
+    DSP_BYTES_PER_TRIAL = 4 * C * T + 4 * C * F * NF
+
+
 UNIT = "trials/s"
 METRIC_TRAIN = "EEG trials/sec (preprocess + train step)"
 METRIC_DSP = "EEG trials/sec (preprocess: FIR + STFT log-spectrogram + z-score)"
@@ -112,65 +134,121 @@ def synth_tokens(B, gen, device=None):
     return ids, labels
 
 
-# --------------------------------------------------------------------------- CPU port (oracle)
-class CpuPort:
-    """Preprocess + train step with stock PyTorch fp32 on the host cores: the oracle's DSP chain
-    (F.conv1d + torch.stft), the oracle's functional encoder, transformers' BART, torch AdamW."""
+# --------------------------------------------------------------------------- stock-PyTorch port (oracle)
+def stock_dsp(x, h, n_fft, hop, log_eps=1.0, z_eps=1e-8):
+    """The DSP spec with the library calls it names (F.conv1d + torch.stft), on whatever device x lives on
+    (same chain as oracle.preprocess_oracle.dsp_torch_cpu_f32)."""
+    Fn = torch.nn.functional
+    B_, C_, T_ = x.shape
+    K = h.numel()
+    y = Fn.conv1d(x.reshape(B_ * C_, 1, T_), h.flip(0).view(1, 1, K), padding=K // 2)
+    spec = torch.stft(y.reshape(B_ * C_, T_), n_fft=n_fft, hop_length=hop, win_length=n_fft,
+                      window=torch.hann_window(n_fft, periodic=True, dtype=x.dtype, device=x.device),
+                      center=True, pad_mode="reflect", normalized=False, onesided=True, return_complex=True)
+    L = torch.log(spec.real ** 2 + spec.imag ** 2 + log_eps)
+    mu = L.mean(dim=(-1, -2), keepdim=True)
+    sd = L.std(dim=(-1, -2), keepdim=True, unbiased=False)
+    return ((L - mu) / (sd + z_eps)).reshape(B_, C_, L.shape[-2], L.shape[-1])
 
-    def __init__(self, workload):
+
+class StockPort:
+    """Preprocess + train step with stock PyTorch kernels: F.conv1d + torch.stft, the oracle's functional
+    encoder (the reference modules restated op for op), transformers' BART, clip_grad_norm_ + torch AdamW.
+    device "cpu": the CPU baseline (fp32, all host threads).  device cuda: BASELINE.md row C6, the same program
+    moved to this B200 -- fp32 or bf16 autocast -- i.e. cuDNN / cuBLAS / ATen instead of libeegx."""
+
+    def __init__(self, workload, device="cpu", batch=None, autocast=False):
         from imagined_speech_translation_b200.preprocess import design_bandpass_fir
-        torch.set_num_threads(os.cpu_count() or 1)
+        self.dev = torch.device(device)
+        self.autocast = autocast
+        if self.dev.type == "cpu":
+            torch.set_num_threads(os.cpu_count() or 1)
         self.workload = workload
-        self.h = torch.from_numpy(design_bandpass_fir(65, (8.0, 30.0), 256.0))
+        self.h = torch.from_numpy(design_bandpass_fir(65, (8.0, 30.0), 256.0)).to(self.dev)
         g = torch.Generator().manual_seed(1234)
         if workload == "dsp":
-            self.B = 32
-            self.x = 20.0 * torch.randn(self.B, C, T, generator=g)
+            self.B = batch or 32
+            self.x = (20.0 * torch.randn(self.B, C, T, generator=g)).to(self.dev)
             return
         from imagined_speech_translation_b200 import trainer as tr
         from imagined_speech_translation_b200.model import EEGDecodingModel
-        self.B = CPU_SAMPLE_B
-        self.x = 20.0 * torch.randn(self.B, C, T, generator=g)
-        self.ids, self.labels = synth_tokens(self.B, g)
+        self.B = batch or (CPU_SAMPLE_B if CONFIG_NAME == "stft" else 8)
+        self.x = (20.0 * torch.randn(self.B, C, T, generator=g)).to(self.dev)
+        ids, labels = synth_tokens(self.B, g)
+        self.ids, self.labels = ids.to(self.dev), labels.to(self.dev)
+        self.ones = torch.ones(self.B, 6, device=self.dev)
         torch.manual_seed(0)
         enc_counts = {k: v * F for k, v in COUNTS.items()}
         self.model = EEGDecodingModel(n_timepoints=NF, region_channel_counts=enc_counts)  # parameter container
         tr.initialize_custom_weights(self.model)
-        self.model.train()
+        self.model.to(self.dev).train()
         self.opt = torch.optim.AdamW(tr.get_optimizer_groups(self.model), eps=1e-8, betas=(0.9, 0.999),
-                                     weight_decay=0.01)
+                                     weight_decay=0.01, fused=self.dev.type == "cuda")
 
-    def step(self):
-        from oracle import encoder_oracle as eo          # bench.py cpu_baseline / reference leg only
-        from oracle import preprocess_oracle as po
-        z = po.dsp_torch_cpu_f32(self.x, self.h, n_fft=N_FFT, hop=HOP)
+    def step(self, sync=True):
+        from oracle import encoder_oracle as eo          # bench.py baseline legs only
+        z = stock_dsp(self.x, self.h, N_FFT, HOP)
         if self.workload == "dsp":
-            return float(z[0, 0, 0, 0])
+            return float(z[0, 0, 0, 0]) if sync else z
         from transformers.modeling_outputs import BaseModelOutput
         xs, c0 = [], 0
         for name in eo.REGIONS:
             xs.append(z[:, c0:c0 + COUNTS[name]].reshape(self.B, -1, NF))
             c0 += COUNTS[name]
         m = self.model
-        feat = eo.brain_encoder(dict(m.brain_encoder.state_dict(keep_vars=True)), xs, train=True)
-        lin, ln = m.bart_decoder.eeg_to_bart[0], m.bart_decoder.eeg_to_bart[1]
-        proj = torch.nn.functional.layer_norm(torch.nn.functional.linear(feat, lin.weight, lin.bias),
-                                              (768,), ln.weight, ln.bias, 1e-5)
-        enc = proj.unsqueeze(1).expand(-1, 6, -1)
-        out = m.bart_decoder.bart(input_ids=None, attention_mask=torch.ones(self.B, 6),
-                                  encoder_outputs=BaseModelOutput(last_hidden_state=enc),
-                                  decoder_input_ids=self.ids, labels=self.labels, return_dict=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.autocast):
+            feat = eo.brain_encoder(dict(m.brain_encoder.state_dict(keep_vars=True)), xs, train=True)
+            lin, ln = m.bart_decoder.eeg_to_bart[0], m.bart_decoder.eeg_to_bart[1]
+            proj = torch.nn.functional.layer_norm(torch.nn.functional.linear(feat, lin.weight, lin.bias),
+                                                  (768,), ln.weight, ln.bias, 1e-5)
+            enc = proj.unsqueeze(1).expand(-1, 6, -1)
+            out = m.bart_decoder.bart(input_ids=None, attention_mask=self.ones,
+                                      encoder_outputs=BaseModelOutput(last_hidden_state=enc),
+                                      decoder_input_ids=self.ids, labels=self.labels, return_dict=True)
         out.loss.backward()
         torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
         self.opt.step()
         self.opt.zero_grad()
-        return float(out.loss)
+        return float(out.loss) if sync else out.loss.detach()
 
     def describe(self, n, secs):
         what = ("F.conv1d + torch.stft" if self.workload == "dsp" else
                 "F.conv1d + torch.stft, oracle encoder, transformers BART, clip + torch AdamW")
         return (f"{self.B} trials x {C} ch x {T} samples per step x {n} steps ({secs:.1f} s), stock PyTorch "
                 f"fp32 CPU: {what}")
+
+
+CpuPort = StockPort
+
+
+def time_torch_b200(dev, steps=5, warmup=2):
+    """the stock-PyTorch program on this B200 at the bench's batch and shape, fp32 and bf16
+    autocast, CUDA events, inputs resident in HBM.  Returns the dict reported as `torch_b200`."""
+    out = {"what": "same preprocess + train step at the same batch and shape with stock PyTorch kernels on this GPU "
+                   "(F.conv1d + torch.stft, the reference encoder restated op for op on torch ops -- cuDNN / cuBLAS "
+                   "/ ATen --, transformers BART, clip_grad_norm_ + fused torch AdamW); dropout off in the encoder "
+                   "(the functional restatement has none), everything else as in `value`",
+           "batch": B_PER_GPU, "unit": UNIT, "steps": steps, "warmup": warmup}
+    for tag, ac in (("fp32", False), ("bf16_autocast", True)):
+        try:
+            port = StockPort("train", device=dev, batch=B_PER_GPU, autocast=ac)
+            for _ in range(warmup):
+                port.step(sync=False)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                loss = port.step(sync=False)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[tag] = {"value": B_PER_GPU / (ms / 1000.0), "ms_per_step": ms, "final_loss": float(loss)}
+        except Exception as exc:                        # report, do not lose the main line
+            out[tag] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        finally:
+            port = None
+            torch.cuda.empty_cache()
+    return out
 
 
 def time_cpu(workload, steps=None, warmup=1, budget_s=15.0):
@@ -192,21 +270,24 @@ def time_cpu(workload, steps=None, warmup=1, budget_s=15.0):
 
 
 def workload_config(workload, extra=None):
+    w = WORKLOADS[CONFIG_NAME]
     if workload == "dsp":
-        cfg = {"workload": "BASELINE configs[1]: preprocessing-only, batch 256 x 64 ch x 2048 samples, STFT "
-                           "n_fft=256 hop=64, FIR 65 taps 8-30 Hz, per GPU"}
+        title = "BASELINE configs[1]" if CONFIG_NAME == "stft" else w["title"] + " (preprocessing only)"
+        cfg = {"workload": f"{title}: preprocessing-only, batch {B_PER_GPU} x {C} ch x {T} samples, STFT "
+                           f"n_fft={N_FFT} hop={HOP}, FIR 65 taps 8-30 Hz, per GPU"}
     else:
-        cfg = {"workload": "BASELINE configs[2]: preprocessing (64 ch x 2048 samples, FIR 65 taps, STFT n_fft=256 "
-                           "hop=64) + full EEG-to-text train step (4 region encoders on (B, 16*129, 33), fusion, "
-                           "BART decoder + LM head + CE, clip + AdamW), bf16 tensor cores / fp32 master weights, "
-                           "batch 256 per GPU, data-parallel",
+        cfg = {"workload": f"{w['title']}: preprocessing ({w['shape']}) + full EEG-to-text train step (4 region "
+                           f"encoders on (B, {COUNTS['frontal']}*{F}, {NF}), fusion, BART decoder + LM head + CE, "
+                           f"clip + AdamW), bf16 tensor cores / fp32 master weights, batch {B_PER_GPU} per GPU, "
+                           "data-parallel",
                "model_params": 0, "tokens_per_trial": L_TOK, "accumulation_steps": 1, "dropout": "on (train mode)",
-               "execution": "preprocess + forward + backward replayed as one CUDA graph; at N > 1 the graph also holds "
-                            "the NCCL all-reduces of the flat gradient buffer, issued slice by slice from inside "
-                            "backward (89 % of the bytes overlap it); fused clip/AdamW launched after the graph"}
+               "execution": "preprocess + forward + backward replayed as one CUDA graph (the four region encoders "
+                            "run in lock step through grouped tcgen05 GEMMs, weight gradients on a side stream); at "
+                            "N > 1 the graph also holds the NCCL all-reduces of the flat gradient buffer, issued "
+                            "slice by slice from inside backward; fused clip/AdamW launched after the graph"}
     cfg.update({"batch_per_gpu": B_PER_GPU, "channels": C, "samples": T, "n_fft": N_FFT, "hop": HOP,
-                "l2": "working set per step (>= 413 MB of trial + feature tensors) exceeds the 126 MB L2; "
-                      "2 rotating input buffers"})
+                "l2": f"working set per step (>= {DSP_BYTES_PER_TRIAL * B_PER_GPU // 1000000} MB of trial + feature "
+                      "tensors) exceeds the 126 MB L2; 2 rotating input buffers"})
     if extra:
         cfg.update(extra)
     return cfg
@@ -221,7 +302,8 @@ def run_reference(args, rank):
         "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * sec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic, random-init weights",
-        "config": workload_config(args.workload, {"sample_batch": CPU_SAMPLE_B if args.workload == "train" else 32}),
+        "config": workload_config(args.workload, {"sample_batch": (CPU_SAMPLE_B if CONFIG_NAME == "stft" else 8)
+                                                  if args.workload == "train" else 32}),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -254,12 +336,15 @@ def bench_dsp(fe, dev, rank, world, args, barrier):
     achieved = DSP_BYTES_PER_TRIAL * B_PER_GPU / (kern_ms * 1e-3) / 1e9
     traffic = None
     try:
+        if CONFIG_NAME != "stft" or fe.kernel_name != "tuned":
+            raise KeyError("no ncu DRAM-traffic capture for this kernel / shape")
         with open(os.path.join(ROOT, "profiles", "dsp_traffic.json")) as fh:
             traffic = json.load(fh).get("dram_bytes_per_launch")
     except Exception:
         pass
     return {"value": B_PER_GPU * world / (ms / 1000.0), "unit": UNIT, "ms_per_step": ms, "steps": steps,
-            "workload": "BASELINE configs[1]: preprocessing-only, 256 x 64 x 2048 per GPU",
+            "workload": f"{'BASELINE configs[1]' if CONFIG_NAME == 'stft' else WORKLOADS[CONFIG_NAME]['title']}: "
+                        f"preprocessing-only, {B_PER_GPU} x {C} x {T} per GPU",
             "gpu_launches": steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": src,
@@ -289,6 +374,7 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     fe = pkg.SpectrogramFrontEnd(C, T, {"n_fft": N_FFT, "hop": HOP})
+    assert (fe.n_freqs, fe.n_frames) == (F, NF)
     sampler = ClockSampler(local_rank) if rank == 0 else None
 
     if args.workload == "dsp":
@@ -431,6 +517,8 @@ def run_ours(args, rank, world, local_rank):
     trainer.release_graph()
     trainer.overlap_allreduce = False                          # no NCCL kernels beside the GEMMs being timed
     model.brain_encoder.parallel_regions = False
+    from imagined_speech_translation_b200 import fused as eegx_fused
+    eegx_fused.DEFER_WGRAD = False                             # weight-gradient GEMMs back on the one stream being timed
     step(batches[0])
     torch.cuda.synchronize()
     torch.cuda._sleep(int(0.15 * 1.9e9))
@@ -456,11 +544,17 @@ def run_ours(args, rank, world, local_rank):
         from imagined_speech_translation_b200 import distributed as dp
         dp.shutdown(trainer)
 
+    torch_arm = None
+    if rank == 0 and world == 1 and not args.no_torch_arm:
+        del trainer, opt, sched
+        torch.cuda.empty_cache()
+        torch_arm = time_torch_b200(dev)
     if rank == 0:
         _, tf_peak, src = measured_peaks()
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
         cpu_val, cores, sample, _ = time_cpu("train", budget_s=15.0)
         print(json.dumps({
+            "torch_b200": torch_arm,
             "metric": METRIC_TRAIN, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic, random-init weights",
@@ -501,7 +595,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="train", choices=["train", "dsp"])
+    ap.add_argument("--config", default="stft", choices=sorted(WORKLOADS),
+                    help="stft = BASELINE configs[2] (default, the configuration the metric is quoted on); "
+                         "long = configs[3] (128 ch x 4096 samples, n_fft 1024 / hop 256)")
+    ap.add_argument("--no-torch-arm", action="store_true", help="skip the stock-PyTorch-on-B200 comparator")
     args = ap.parse_args()
+    select_config(args.config)
     if args.impl == "ours":
         args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

@@ -13,6 +13,8 @@ fe = pkg.SpectrogramFrontEnd(C, T)
 torch.manual_seed(0)
 model = EEGDecodingModel(n_timepoints=fe.n_frames, region_channel_counts={k: v * fe.n_freqs for k, v in counts.items()}).cuda().train()
 model.brain_encoder.parallel_regions = False
+from imagined_speech_translation_b200 import fused
+fused.DEFER_WGRAD = False      # one stream: an event pair brackets exactly one GEMM
 cfg = dict(tr.CONFIG, accumulation_steps=1)
 opt = tr.build_optimizer(model, cfg)
 t = tr.EEGTrainer(model, None, None, None, opt, tr.cosine_schedule_with_warmup(opt, 2, 1000), cfg, front_end=fe, region_channel_counts=counts)
