@@ -36,6 +36,7 @@ SIGNATURES = {
     "eegx_dsp_plan_dims": (C.c_int, [C.c_void_p, c_int_p, c_int_p]),
     "eegx_dsp_plan_kernel": (C.c_int, [C.c_void_p]),
     "eegx_dsp_plan_force_generic": (C.c_int, [C.c_void_p, C.c_int]),
+    "eegx_dsp_plan_set_precise": (C.c_int, [C.c_void_p, C.c_int]),
     "eegx_dsp_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                    C.c_int64, C.c_void_p]),
 }
@@ -110,6 +111,8 @@ SIGNATURES.update({
     "eegx_ce_bwd_bf16": (_I, [_P, _I64, _P, _P, _P, _P, _I64, _I64, _I64, _P]),
     "eegx_attn_fwd_bf16": (_I, [C.POINTER(AttnDesc), _P, _P, _P, _P, _P] + _RNG + [_P]),
     "eegx_attn_bwd_bf16": (_I, [C.POINTER(AttnDesc)] + [_P] * 9 + [_I64, _I64, _I64] + _RNG + [_P]),
+    "eegx_attn_flash_fwd_bf16": (_I, [C.POINTER(AttnDesc), _P, _P, _P, _P, _P] + _RNG + [_P]),
+    "eegx_attn_flash_bwd_bf16": (_I, [C.POINTER(AttnDesc)] + [_P] * 10 + [_I64, _I64, _I64] + _RNG + [_P]),
 })
 
 

@@ -27,6 +27,7 @@ extern "C" int eegx_dsp_plan_create(eegx_dsp_plan** out_plan, int C, int T, int 
     p->n_frames = 1 + T / hop;
     p->log_eps = log_eps; p->z_eps = z_eps;
     p->force_generic = 0;
+    p->precise = 0;
     {
         const char* v = getenv("EEGX_DSP_VARIANT");
         p->tuned_variant = v ? atoi(v) : 0;
@@ -65,10 +66,11 @@ extern "C" int eegx_dsp_plan_create(eegx_dsp_plan** out_plan, int C, int T, int 
         delete p;
         return eegx::set_error(EEGX_ERR_CUDA, "cudaMemcpy(tables): %s", cudaGetErrorString(e));
     }
-    p->kernel = eegx::dsp_tuned_supported(p) ? 1 : 0;
-    if (p->kernel == 1) {
-        std::vector<float> lt(eegx::dsp_tuned_table_floats());
-        eegx::dsp_tuned_fill_tables(lt.data());
+    p->kernel = eegx::dsp_tuned_supported(p) ? 1 : (eegx::dsp_long_supported(p) ? 2 : 0);
+    if (p->kernel != 0) {
+        std::vector<float> lt(p->kernel == 1 ? eegx::dsp_tuned_table_floats() : eegx::dsp_long_table_floats());
+        if (p->kernel == 1) eegx::dsp_tuned_fill_tables(lt.data());
+        else eegx::dsp_long_fill_tables(lt.data());
         e = cudaMalloc(&p->d_lane_tables, lt.size() * sizeof(float));
         if (e == cudaSuccess)
             e = cudaMemcpy(p->d_lane_tables, lt.data(), lt.size() * sizeof(float), cudaMemcpyHostToDevice);
@@ -100,12 +102,23 @@ extern "C" int eegx_dsp_plan_dims(const eegx_dsp_plan* plan, int* F, int* N_f) {
 
 extern "C" int eegx_dsp_plan_kernel(const eegx_dsp_plan* plan) {
     EEGX_REQUIRE(plan, EEGX_ERR_ARG, "plan is NULL");
-    return (plan->kernel == 1 && !plan->force_generic) ? 1 : 0;
+    return plan->precise ? 3 : (plan->force_generic ? 0 : plan->kernel);
 }
 
 extern "C" int eegx_dsp_plan_force_generic(eegx_dsp_plan* plan, int on) {
     EEGX_REQUIRE(plan, EEGX_ERR_ARG, "plan is NULL");
     plan->force_generic = on ? 1 : 0;
+    return EEGX_OK;
+}
+
+extern "C" int eegx_dsp_plan_set_precise(eegx_dsp_plan* plan, int on) {
+    EEGX_REQUIRE(plan, EEGX_ERR_ARG, "plan is NULL");
+    if (on) {
+        const size_t smem = eegx::dsp_precise_smem_bytes(plan->T, plan->n_fft, plan->hop, plan->numtaps);
+        EEGX_REQUIRE(smem <= 227 * 1024, EEGX_ERR_SHAPE, "float64 DSP kernel: T=%d / n_fft=%d need %zu bytes of "
+                     "shared memory per CTA (> 227 KB)", plan->T, plan->n_fft, smem);
+    }
+    plan->precise = on ? 1 : 0;
     return EEGX_OK;
 }
 
@@ -139,8 +152,11 @@ extern "C" int eegx_dsp_forward(const eegx_dsp_plan* plan, const float* x, const
     a.window = plan->d_tables + plan->off_window;
     a.twiddle = reinterpret_cast<const float2*>(plan->d_tables + plan->off_twiddle);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (plan->precise) return eegx::launch_dsp_precise(plan, a, st);
     // windowed mode (arbitrary, possibly unaligned onsets) always takes the generic kernel
     if (plan->kernel == 1 && !plan->force_generic && onsets == nullptr)
         return eegx::launch_dsp_tuned(plan, a, st);
+    if (plan->kernel == 2 && !plan->force_generic && onsets == nullptr)
+        return eegx::launch_dsp_long(plan, a, st);
     return eegx::launch_dsp_generic(plan, a, st);
 }

@@ -7,12 +7,13 @@ struct eegx_dsp_plan {
     int F, n_frames;
     float log_eps, z_eps;
     int device;
-    int kernel;          // 0 generic, 1 tuned (n_fft 256 / hop 64 / 65 taps / T % 64 == 0)
+    int kernel;          // 0 generic, 1 tuned (T 2048 / n_fft 256 / hop 64 / 65 taps), 2 long (T 4096 / n_fft 1024 / hop 256 / 65 taps)
     int force_generic;
+    int precise;         // float64 arithmetic (dsp_precise.cu); overrides every other choice
     int tuned_variant;   // tile shape of the tuned kernel (EEGX_DSP_VARIANT, default 0 = auto)
     // device tables, one allocation: taps[numtaps] | pad to 4 | window[n_fft] | twiddle float2[n_fft/2]
     float* d_tables;
-    float* d_lane_tables;  // tuned kernel only: [8][60] per-lane window / twiddle constants
+    float* d_lane_tables;  // tuned kernels only: per-lane window / twiddle constants
     int off_window, off_twiddle, table_floats;
     float h_taps[132];
     size_t smem_generic;
@@ -42,5 +43,15 @@ int launch_dsp_tuned(const eegx_dsp_plan* plan, const DspArgs& a, cudaStream_t s
 int launch_dsp_pair(const eegx_dsp_plan* plan, const DspArgs& a, cudaStream_t st);
 int dsp_tuned_table_floats();
 void dsp_tuned_fill_tables(float* host);
+
+// Float64 variant of the generic kernel (eegx_dsp_plan_set_precise).
+int launch_dsp_precise(const eegx_dsp_plan* plan, const DspArgs& a, cudaStream_t st);
+size_t dsp_precise_smem_bytes(int T, int n_fft, int hop, int numtaps);
+
+// Tuned kernel for T = 4096, n_fft = 1024, hop = 256, 65 taps (BASELINE config 4).
+bool dsp_long_supported(const eegx_dsp_plan* plan);
+int launch_dsp_long(const eegx_dsp_plan* plan, const DspArgs& a, cudaStream_t st);
+int dsp_long_table_floats();
+void dsp_long_fill_tables(float* host);
 
 }  // namespace eegx

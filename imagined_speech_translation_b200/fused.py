@@ -544,7 +544,13 @@ ATTN_HEAD_DIMS = (64, 96, 128, 192)
 
 
 def attn_supported(Sq: int, Sk: int, hd: int) -> bool:
-    return 1 <= Sq <= ATTN_MAX_S and 1 <= Sk <= ATTN_MAX_S and hd in ATTN_HEAD_DIMS
+    """Sequences up to ATTN_MAX_S tokens run the one-CTA-per-(batch, head) kernel, longer ones the flash kernel
+    (keys / values streamed in tiles, scores never in HBM); both need a head_dim in ATTN_HEAD_DIMS."""
+    return Sq >= 1 and Sk >= 1 and hd in ATTN_HEAD_DIMS
+
+
+def _attn_is_flash(Sq: int, Sk: int) -> bool:
+    return Sq > ATTN_MAX_S or Sk > ATTN_MAX_S
 
 
 def _attn_desc(B, H, Sq, Sk, hd, q, k, v, o, causal):
@@ -574,9 +580,9 @@ class _AttnCore(torch.autograd.Function):
         o = torch.empty(B * Sq, d_model, dtype=torch.bfloat16, device=q.device)
         lse = torch.empty(B * H * Sq, dtype=torch.float32, device=q.device)
         desc = _attn_desc(B, H, Sq, Sk, hd, q, k, v, o, causal)
-        _lib.check(_lib.lib().eegx_attn_fwd_bf16(C.byref(desc), _lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(o),
-                                                 _lib.ptr(lse), _lib.ptr(rng), site, p, _lib.stream_ptr()),
-                   "eegx_attn_fwd_bf16")
+        fwd = "eegx_attn_flash_fwd_bf16" if _attn_is_flash(Sq, Sk) else "eegx_attn_fwd_bf16"
+        _lib.check(getattr(_lib.lib(), fwd)(C.byref(desc), _lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(o),
+                                            _lib.ptr(lse), _lib.ptr(rng), site, p, _lib.stream_ptr()), fwd)
         ctx.save_for_backward(q_or_qkv, kv, o, lse)
         ctx.cfg = (B, Sq, Sk, H, causal, rng, site, p)
         return o
@@ -600,6 +606,13 @@ class _AttnCore(torch.autograd.Function):
             dq, dk, dv = dpacked, dkv[:, :d_model], dkv[:, d_model:]
         hd = d_model // H
         desc = _attn_desc(B, H, Sq, Sk, hd, q, k, v, o, causal)
+        if _attn_is_flash(Sq, Sk):
+            dsum = torch.empty_like(lse)                 # D_i = dO_i . O_i, written by the dQ kernel
+            _lib.check(_lib.lib().eegx_attn_flash_bwd_bf16(
+                C.byref(desc), _lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(o), _lib.ptr(do), _lib.ptr(lse),
+                _lib.ptr(dsum), _lib.ptr(dq), _lib.ptr(dk), _lib.ptr(dv), dq.stride(0), dk.stride(0), dv.stride(0),
+                _lib.ptr(rng), site, p, _lib.stream_ptr()), "eegx_attn_flash_bwd_bf16")
+            return dpacked, dkv, None, None, None, None, None, None, None, None
         _lib.check(_lib.lib().eegx_attn_bwd_bf16(
             C.byref(desc), _lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(o), _lib.ptr(do), _lib.ptr(lse),
             _lib.ptr(dq), _lib.ptr(dk), _lib.ptr(dv), dq.stride(0), dk.stride(0), dv.stride(0), _lib.ptr(rng), site, p,

@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import fused, nn_ops
+from . import _lib, fused, nn_ops
 from .nn_ops import PAD
 
 
@@ -69,8 +69,8 @@ def _mha(mod: nn.MultiheadAttention, q_in, kv_in, self_attn: bool):
     """nn.MultiheadAttention(batch_first=True) semantics (packed in_proj, q scaled by
     1/sqrt(head_dim), softmax, dropout on the probabilities in train mode, out_proj); the
     head-averaged attention weights the reference discards are not produced.  Sequences up to 64
-    tokens run the fused attention core (probabilities stay on the SM); longer ones fall back to
-    batched GEMMs with the scores in HBM."""
+    tokens run the one-CTA-per-(batch, head) attention core, longer ones (the raw front end: S = T + 4 =
+    1655 / 2052 / 4100) the flash kernel; either way the scores and probabilities stay on the SM."""
     B, Sq, d = q_in.shape
     H = mod.num_heads
     hd = d // H
@@ -85,22 +85,8 @@ def _mha(mod: nn.MultiheadAttention, q_in, kv_in, self_attn: bool):
             kv = nn_ops.linear(kv_in.reshape(B * Sk, d), W[d:], b[d:])
             o = fused.attn_cross(q, kv, B, Sq, Sk, H, p=mod.dropout, training=mod.training)
         return nn_ops.linear(o, mod.out_proj.weight, mod.out_proj.bias).view(B, Sq, d)
-    if self_attn:
-        qkv = nn_ops.linear(q_in, W, b)                              # (B, S, 3d)
-        q, k, v = qkv.split(d, dim=-1)
-    else:
-        q = nn_ops.linear(q_in, W[:d], b[:d])
-        kv = nn_ops.linear(kv_in, W[d:], b[d:])
-        k, v = kv.split(d, dim=-1)
-    q = q.reshape(B, Sq, H, hd).transpose(1, 2)
-    k = k.reshape(B, Sk, H, hd).transpose(1, 2)
-    v = v.reshape(B, Sk, H, hd).transpose(1, 2)
-    scores = torch.matmul(q, k.transpose(-1, -2)).float() * (1.0 / math.sqrt(hd))
-    p = torch.softmax(scores, dim=-1)
-    if mod.training and mod.dropout > 0.0:
-        p = F.dropout(p, mod.dropout)
-    o = torch.matmul(p.to(v.dtype), v).transpose(1, 2).reshape(B, Sq, d)
-    return nn_ops.linear(o, mod.out_proj.weight, mod.out_proj.bias)
+    raise _lib.EegxError(f"attention head_dim {hd} is not one the fused attention kernels serve "
+                         f"{fused.ATTN_HEAD_DIMS}; there is no library fallback")
 
 
 def _layer_norm(x, ln: nn.LayerNorm):

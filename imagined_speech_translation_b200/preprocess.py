@@ -107,10 +107,15 @@ class SpectrogramFrontEnd:
 
     @property
     def kernel_name(self) -> str:
-        return "tuned" if _lib.lib().eegx_dsp_plan_kernel(self._plan) == 1 else "generic"
+        return ("generic", "tuned", "long", "precise")[_lib.lib().eegx_dsp_plan_kernel(self._plan)]
 
     def force_generic(self, on: bool = True) -> None:
         _lib.check(_lib.lib().eegx_dsp_plan_force_generic(self._plan, int(on)))
+
+    def set_precise(self, on: bool = True) -> None:
+        """float64 arithmetic between the float32 input and output (about 10x slower; the bound of the spec at
+        n_fft = 1024, where float32 stops at 1.1e-5 .. 1.9e-5)."""
+        _lib.check(_lib.lib().eegx_dsp_plan_set_precise(self._plan, int(on)))
 
     def out_shape(self, batch: int):
         return (batch, self.n_channels, self.n_freqs, self.n_frames)

@@ -92,10 +92,15 @@ int eegx_dsp_plan_create(eegx_dsp_plan** plan, int C, int T, int n_fft, int hop,
                          const float* fir, int numtaps, float log_eps, float z_eps);
 int eegx_dsp_plan_destroy(eegx_dsp_plan* plan);
 int eegx_dsp_plan_dims(const eegx_dsp_plan* plan, int* F, int* N_f);
-/* Which kernel the plan dispatches to: 0 = generic, 1 = tuned n_fft=256/hop=64/K=65. */
+/* Which kernel the plan dispatches to: 0 = generic, 1 = tuned T=2048/n_fft=256/hop=64/K=65 (BASELINE configs[1-2]),
+ * 2 = tuned T=4096/n_fft=1024/hop=256/K=65 (configs[3]), 3 = float64 (set_precise). */
 int eegx_dsp_plan_kernel(const eegx_dsp_plan* plan);
 /* Force the generic kernel (testing / A-B comparison). */
 int eegx_dsp_plan_force_generic(eegx_dsp_plan* plan, int on);
+/* Run the chain in float64 (FIR accumulation, FFT butterflies, log, statistics; float32 in and out).  About a
+ * tenth of the tuned kernels' throughput; reaches the spec's 1e-5 bound at n_fft = 1024, where float32 arithmetic
+ * measures 1.1e-5 .. 1.9e-5 against float64. */
+int eegx_dsp_plan_set_precise(eegx_dsp_plan* plan, int on);
 
 /* onsets == NULL: x is (B, C, T), trials already cut.
  * onsets != NULL: x is one continuous recording (C, rec_len) and
@@ -310,6 +315,18 @@ int eegx_attn_bwd_bf16(const eegx_attn_desc* d, const void* q, const void* k, co
                        const void* d_o, const float* lse, void* dq, void* dk, void* dv, int64_t dq_rs, int64_t dk_rs,
                        int64_t dv_rs, const uint64_t* rng_state, uint32_t site, float p, void* stream);
 
+/* The same attention core for LONG sequences (any S_q, S_k, no causal mask): flash style -- keys / values stream
+ * through shared memory in tiles of 64, online softmax, the S_q x S_k scores and probabilities never exist in HBM
+ * (main_model/src/models/layers.py:230-251 at the reference's real shapes, S = T + 4 = 1655 / 2052 / 4100, where
+ * nn.MultiheadAttention materialises B*H*S*S scores).  Same descriptor and addressing as above.  Backward
+ * recomputes the probabilities from lse; `dsum` is a caller-owned (B, H, S_q) fp32 workspace (D_i = dO_i . O_i,
+ * written by the dQ kernel, read by the dK/dV kernel).  Every gradient has one owner CTA: bit-reproducible. */
+int eegx_attn_flash_fwd_bf16(const eegx_attn_desc* d, const void* q, const void* k, const void* v, void* o, float* lse,
+                             const uint64_t* rng_state, uint32_t site, float p, void* stream);
+int eegx_attn_flash_bwd_bf16(const eegx_attn_desc* d, const void* q, const void* k, const void* v, const void* o,
+                             const void* d_o, const float* lse, float* dsum, void* dq, void* dk, void* dv, int64_t dq_rs,
+                             int64_t dk_rs, int64_t dv_rs, const uint64_t* rng_state, uint32_t site, float p,
+                             void* stream);
 
 /* ------------------------------------------------------------------------
  * Cross-entropy at the loss end of the train step (main_model/src/models/bart_decoder.py:41-48 ->

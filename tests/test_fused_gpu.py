@@ -259,10 +259,54 @@ def test_attention_cross(B, Sq, Sk, H, hd):
     assert rel(kv.grad.view(B, Sk, 2 * d), kvr.grad) <= 2e-2
 
 
-def test_attention_dropout_is_consistent():
+@pytest.mark.parametrize("B,S,H,hd", [(2, 65, 4, 192), (1, 1655, 8, 96), (2, 200, 4, 192), (1, 129, 12, 64),
+                                      (1, 2052, 4, 192), (3, 100, 6, 128)])
+def test_flash_attention_self(B, S, H, hd):
+    """S > 64: the flash kernels (csrc/attn_flash.cu), ragged last tiles included (1655 = T + 4 of the real data)."""
+    d = H * hd
+    g = torch.Generator(device="cuda").manual_seed(S * H)
+    qkv = bf(torch.randn(B * S, 3 * d, device="cuda", generator=g)).requires_grad_(True)
+    do = bf(torch.randn(B * S, d, device="cuda", generator=g))
+    o = fused.attn_self(qkv, B, S, H)
+    o.backward(do)
+    r = qkv.detach().float().view(B, S, 3 * d).requires_grad_(True)
+    ref = _ref_attn(r[..., :d], r[..., d:2 * d], r[..., 2 * d:], H, False)
+    ref.backward(do.float().view(B, S, d))
+    assert rel(o.view(B, S, d), ref) <= 1.5e-2
+    gq, gr = qkv.grad.view(B, S, 3 * d), r.grad
+    for lo in (0, d, 2 * d):                     # dq, dk, dv separately: their scales differ by orders of magnitude
+        assert rel(gq[..., lo:lo + d], gr[..., lo:lo + d]) <= 2e-2
+    # bit-reproducible (one owner CTA per gradient element, fixed summation order)
+    q2 = qkv.detach().clone().requires_grad_(True)
+    o2 = fused.attn_self(q2, B, S, H)
+    o2.backward(do)
+    assert torch.equal(o, o2) and torch.equal(qkv.grad, q2.grad)
+
+
+@pytest.mark.parametrize("B,Sq,Sk,H,hd", [(2, 300, 70, 4, 192), (1, 40, 1000, 8, 96), (2, 130, 131, 4, 64)])
+def test_flash_attention_cross(B, Sq, Sk, H, hd):
+    d = H * hd
+    g = torch.Generator(device="cuda").manual_seed(Sq * Sk)
+    q = bf(torch.randn(B * Sq, d, device="cuda", generator=g)).requires_grad_(True)
+    kv = bf(torch.randn(B * Sk, 2 * d, device="cuda", generator=g)).requires_grad_(True)
+    do = bf(torch.randn(B * Sq, d, device="cuda", generator=g))
+    o = fused.attn_cross(q, kv, B, Sq, Sk, H)
+    o.backward(do)
+    qr = q.detach().float().view(B, Sq, d).requires_grad_(True)
+    kvr = kv.detach().float().view(B, Sk, 2 * d).requires_grad_(True)
+    ref = _ref_attn(qr, kvr[..., :d], kvr[..., d:], H, False)
+    ref.backward(do.float().view(B, Sq, d))
+    assert rel(o.view(B, Sq, d), ref) <= 1.5e-2
+    assert rel(q.grad.view(B, Sq, d), qr.grad) <= 2e-2
+    assert rel(kv.grad.view(B, Sk, 2 * d)[..., :d], kvr.grad[..., :d]) <= 2e-2
+    assert rel(kv.grad.view(B, Sk, 2 * d)[..., d:], kvr.grad[..., d:]) <= 2e-2
+
+
+@pytest.mark.parametrize("S", [37, 150])
+def test_attention_dropout_is_consistent(S):
     """With dropout on, backward must use the forward mask: check dV against the dropped probabilities
-    recovered from the forward output (v = identity-like trick)."""
-    B, S, H, hd = 2, 37, 4, 64
+    recovered from the forward output (v = identity-like trick).  S = 150 exercises the flash kernels."""
+    B, H, hd = 2, 4, 64
     d = H * hd
     fused.set_seed(7)
     g = torch.Generator(device="cuda").manual_seed(3)
@@ -291,3 +335,9 @@ def test_attention_dropout_is_consistent():
     fd = (fs[0] - fs[1]) / (2 * eps)
     an = (x.grad.float() * dirn.float()).sum().item()
     assert abs(fd - an) <= 0.08 * max(abs(fd), abs(an), 1.0)
+    # keep rate of the probabilities: with v = 1 the output is sum_j p_ij m_ij, whose mean is 1
+    fused.begin_step()
+    ones = qkv.clone()
+    ones[:, 2 * d:] = 1.0
+    o3 = fused.attn_self(ones, B, S, H, p=0.25, training=True).float()
+    assert abs(o3.mean().item() - 1.0) <= 0.02

@@ -185,11 +185,11 @@ def _zero_dropout(model):
 
 def test_high_density_long_window_step():
     """BASELINE configs[3] shape at a small batch: 128 ch x 4096 samples, STFT n_fft=1024 hop=256
-    (generic DSP kernel) -> 4 regions of 32 x 513 feature channels x 17 frames -> one train step."""
+    (long-window DSP kernel) -> 4 regions of 32 x 513 feature channels x 17 frames -> one train step."""
     C, T, B = 128, 4096, 2
     counts = {'frontal': 32, 'temporal': 32, 'central': 32, 'parietal': 32}
     fe = pkg.SpectrogramFrontEnd(C, T, pkg.DSP_CONFIG_LONG)
-    assert (fe.n_freqs, fe.n_frames) == (513, 17) and fe.kernel_name == "generic"
+    assert (fe.n_freqs, fe.n_frames) == (513, 17) and fe.kernel_name == "long"
     torch.manual_seed(0)
     model = EEGDecodingModel(n_timepoints=fe.n_frames,
                              region_channel_counts={k: v * fe.n_freqs for k, v in counts.items()}).cuda().train()
