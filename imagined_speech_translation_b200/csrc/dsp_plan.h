@@ -41,6 +41,7 @@ size_t dsp_generic_smem_bytes(int T, int n_fft, int hop, int numtaps);
 bool dsp_tuned_supported(const eegx_dsp_plan* plan);
 int launch_dsp_tuned(const eegx_dsp_plan* plan, const DspArgs& a, cudaStream_t st);
 int launch_dsp_pair(const eegx_dsp_plan* plan, const DspArgs& a, cudaStream_t st);
+int launch_dsp_umma(const eegx_dsp_plan* plan, const DspArgs& a, cudaStream_t st);   // FIR on tcgen05 (dsp_umma.cu)
 int dsp_tuned_table_floats();
 void dsp_tuned_fill_tables(float* host);
 

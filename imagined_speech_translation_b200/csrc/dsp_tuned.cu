@@ -632,6 +632,7 @@ int launch_dsp_tuned(const eegx_dsp_plan* plan, const DspArgs& d, cudaStream_t s
         case 4: return launch_variant<1, 96, true>(a, st);   // 1 row per tile, packed half-row FIR
         case 5: return launch_variant<1, 96, false, true>(a, st);    // 1 row per tile, FIR as 3xTF32 Toeplitz MMAs
         case 6: return launch_variant<1, 128, false, true>(a, st);   // same, 4 warps (16 FIR blocks divide evenly)
+        case 7: return launch_dsp_umma(plan, d, st);    // FIR as tcgen05 kind::tf32 Toeplitz MMAs, operands in tensor memory (dsp_umma.cu)
         case 1: return launch_variant<1, 96>(a, st);    // 4 CTAs/SM x 3 warps, 1 row per tile
         case 2: return launch_variant<2, 192>(a, st);   // 2 CTAs/SM x 6 warps, 2 rows per tile
         default: return launch_variant<1, 96>(a, st);
