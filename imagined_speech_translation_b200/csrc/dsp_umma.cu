@@ -104,8 +104,41 @@ struct UmmaArgs {
         }                                                         \
     } while (0)
 
-// Forward 16-point FFT, natural order in and out.
-__device__ __forceinline__ void fft16(const cf (&c)[16], cf (&out)[16]) {
+// ---- packed f32x2 arithmetic: one instruction works on two independent FFTs (or two bins) at once ----
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk(f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2 bc(float x) { return pk(x, x); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+struct c2 { f2 r, i; };   // two complex values: low halves = FFT (or bin) A, high halves = FFT (or bin) B
+__device__ __forceinline__ c2 cadd(c2 a, c2 b) { return {add2(a.r, b.r), add2(a.i, b.i)}; }
+__device__ __forceinline__ c2 csub(c2 a, c2 b) { return {sub2(a.r, b.r), sub2(a.i, b.i)}; }
+__device__ __forceinline__ c2 cadd_mni(c2 x, c2 a) { return {add2(x.r, a.i), sub2(x.i, a.r)}; }   // x + (-i) a
+__device__ __forceinline__ c2 csub_mni(c2 x, c2 a) { return {sub2(x.r, a.i), add2(x.i, a.r)}; }   // x - (-i) a
+__device__ __forceinline__ c2 cmul2(c2 a, f2 wr, f2 wi) {                                           // a * (wr + i wi)
+    return {sub2(mul2(a.r, wr), mul2(a.i, wi)), fma2(a.r, wi, mul2(a.i, wr))};
+}
+
+// Two forward 8-point FFTs in lockstep (e^{-i...}), in place, natural order in and out.
+__device__ __forceinline__ void fft8p(c2 (&v)[8]) {
+    const f2 rs = bc(RSQRT2), nrs = bc(-RSQRT2);
+    const c2 e0 = cadd(v[0], v[4]), e1 = cadd(v[1], v[5]), e2 = cadd(v[2], v[6]), e3 = cadd(v[3], v[7]);
+    const c2 d0 = csub(v[0], v[4]), d1 = csub(v[1], v[5]), d2 = csub(v[2], v[6]), d3 = csub(v[3], v[7]);
+    const c2 o1 = {mul2(add2(d1.r, d1.i), rs), mul2(sub2(d1.i, d1.r), rs)};      // d1 * W8^1
+    const c2 o3 = {mul2(sub2(d3.i, d3.r), rs), mul2(add2(d3.r, d3.i), nrs)};     // d3 * W8^3
+    const c2 s0 = cadd(e0, e2), s1 = csub(e0, e2), s2 = cadd(e1, e3), s3 = csub(e1, e3);
+    v[0] = cadd(s0, s2); v[4] = csub(s0, s2); v[2] = cadd_mni(s1, s3); v[6] = csub_mni(s1, s3);
+    const c2 t0 = cadd_mni(d0, d2), t1 = csub_mni(d0, d2), t2 = cadd(o1, o3), t3 = csub(o1, o3);
+    v[1] = cadd(t0, t2); v[5] = csub(t0, t2); v[3] = cadd_mni(t1, t3); v[7] = csub_mni(t1, t3);
+}
+
+// Forward 16-point FFT of c[0..15]; the result comes back as pairs: out[k] = (X[2k], X[2k + 1]).  The even /
+// odd split and the odd half's twiddles are scalar, the two 8-point FFTs run packed.
+__device__ __forceinline__ void fft16p(const cf (&c)[16], c2 (&out)[8]) {
     constexpr float C1 = 0.92387953251128675613f, S1 = 0.38268343236508977173f;  // cos/sin(pi/8)
     cf e[8], o[8];
 #pragma unroll
@@ -120,13 +153,9 @@ __device__ __forceinline__ void fft16(const cf (&c)[16], cf (&out)[16]) {
     o[5] = cmul(o[5], -S1, -C1);
     o[6] = {(o[6].i - o[6].r) * RSQRT2, -(o[6].r + o[6].i) * RSQRT2};
     o[7] = cmul(o[7], -C1, -S1);
-    fft8(e);
-    fft8(o);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        out[2 * k] = e[k];
-        out[2 * k + 1] = o[k];
-    }
+    for (int n = 0; n < 8; ++n) out[n] = {pk(e[n].r, o[n].r), pk(e[n].i, o[n].i)};
+    fft8p(out);
 }
 
 // ---- tcgen05 helpers ----
@@ -245,6 +274,9 @@ __device__ __forceinline__ void issue_fir(unsigned tmem_base, unsigned bhi_addr,
     umma_commit(bar);
 }
 
+// position of extended sample p inside its aligned group of four: (0, 1, 2, 3) -> (0, 2, 1, 3)
+__device__ __forceinline__ int perm4(int p) { return (p & ~3) | ((p & 1) << 1) | ((p >> 1) & 1); }
+
 // warps 0-7: D -> reflect-extended rows in shared memory.  Warp w: lane quarter w & 3, columns [32 (w >> 2), +32).
 __device__ __forceinline__ void readout_tile(float* ys, unsigned tmem_base, int warp, int lane) {
     const int q = warp & 3, half = warp >> 2;
@@ -256,20 +288,20 @@ __device__ __forceinline__ void readout_tile(float* ys, unsigned tmem_base, int 
     float4* dst = reinterpret_cast<float4*>(yrow + 128 + t0);
 #pragma unroll
     for (int c = 0; c < 8; ++c)
-        dst[c] = make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]), __uint_as_float(r[4 * c + 2]),
-                             __uint_as_float(r[4 * c + 3]));
+        dst[c] = make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 2]), __uint_as_float(r[4 * c + 1]),
+                             __uint_as_float(r[4 * c + 3]));      // (t, t+2, t+1, t+3): see the STFT loads
     if (t0 <= 128) {          // reflect copy on the left: index -t for t in [1, 128]
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
             const int t = t0 + e;
-            if (t >= 1 && t <= 128) yrow[128 - t] = __uint_as_float(r[e]);
+            if (t >= 1 && t <= 128) yrow[perm4(128 - t)] = __uint_as_float(r[e]);
         }
     }
     if (t0 + 31 >= T - 129) {   // reflect copy on the right: index 2(T-1)-t for t in [T-129, T-2]
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
             const int t = t0 + e;
-            if (t >= T - 129 && t <= T - 2) yrow[2 * (T - 1) - t + 128] = __uint_as_float(r[e]);
+            if (t >= T - 129 && t <= T - 2) yrow[perm4(2 * (T - 1) - t + 128)] = __uint_as_float(r[e]);
         }
     }
 }
@@ -306,22 +338,25 @@ __global__ void __launch_bounds__(NT, 1) dsp_umma_kernel(const __grid_constant__
     const bool ctrl = warp == CTRL_WARP;
 
     // per-lane constants (fixed for the lifetime of the CTA)
-    float win[16], twr[2][7], twi[2][7], spr[8], spi[8];
+    // packed: window pairs (samples 0 | 2 and 1 | 3 of a group of four), stage-1 twiddles of the lane's two
+    // 8-point FFTs, split-step twiddles of two neighbouring bins
+    f2 winr[4], wini[4], twr[7], twi[7], spr[4], spi[4];
     {
         const float* tb = a.lane_tables + g * LANE_TABLE;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) win[i] = __ldg(tb + i);
+        for (int i = 0; i < 4; ++i) {
+            winr[i] = pk(__ldg(tb + 4 * i + 0), __ldg(tb + 4 * i + 2));
+            wini[i] = pk(__ldg(tb + 4 * i + 1), __ldg(tb + 4 * i + 3));
+        }
 #pragma unroll
-        for (int e = 0; e < 2; ++e)
+        for (int k = 0; k < 7; ++k) {
+            twr[k] = pk(__ldg(tb + 16 + k * 2), __ldg(tb + 16 + (7 + k) * 2));
+            twi[k] = pk(__ldg(tb + 16 + k * 2 + 1), __ldg(tb + 16 + (7 + k) * 2 + 1));
+        }
 #pragma unroll
-            for (int k = 0; k < 7; ++k) {
-                twr[e][k] = __ldg(tb + 16 + (e * 7 + k) * 2);
-                twi[e][k] = __ldg(tb + 16 + (e * 7 + k) * 2 + 1);
-            }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            spr[k] = __ldg(tb + 44 + 2 * k);
-            spi[k] = __ldg(tb + 44 + 2 * k + 1);
+        for (int j = 0; j < 4; ++j) {
+            spr[j] = pk(__ldg(tb + 44 + 4 * j), __ldg(tb + 44 + 4 * j + 2));
+            spi[j] = pk(__ldg(tb + 44 + 4 * j + 1), __ldg(tb + 44 + 4 * j + 3));
         }
     }
 
@@ -436,43 +471,42 @@ __global__ void __launch_bounds__(NT, 1) dsp_umma_kernel(const __grid_constant__
             const int m = full ? (task & 7) + 8 * q : 32;
             const float* yseg = ys + r * YS_PITCH + m * 64;  // extended position 64 m
 
-            cf z0[8], z1[8];
+            // ys holds every aligned group of four samples as (t, t+2, t+1, t+3): a 128-bit load is the packed pair
+            // (re | re, im | im) of the lane's two interleaved 8-point FFTs, z[n] = y[2n] + i y[2n+1]
+            c2 P[8];
 #pragma unroll
             for (int aa = 0; aa < 8; ++aa) {
-                const float4 u = *reinterpret_cast<const float4*>(yseg + aa * 32 + 4 * g);
-                float v0, v1, v2, v3;
+                const ulonglong2 u = *reinterpret_cast<const ulonglong2*>(yseg + aa * 32 + 4 * g);
                 if (aa < 4) {
-                    v0 = u.x * win[aa * 4 + 0]; v1 = u.y * win[aa * 4 + 1];
-                    v2 = u.z * win[aa * 4 + 2]; v3 = u.w * win[aa * 4 + 3];
+                    P[aa] = {mul2(u.x, winr[aa]), mul2(u.y, wini[aa])};
                 } else {   // hann[n + 128] = 1 - hann[n]
-                    v0 = fmaf(-u.x, win[(aa - 4) * 4 + 0], u.x); v1 = fmaf(-u.y, win[(aa - 4) * 4 + 1], u.y);
-                    v2 = fmaf(-u.z, win[(aa - 4) * 4 + 2], u.z); v3 = fmaf(-u.w, win[(aa - 4) * 4 + 3], u.w);
+                    P[aa] = {sub2(u.x, mul2(u.x, winr[aa - 4])), sub2(u.y, mul2(u.y, wini[aa - 4]))};
                 }
-                z0[aa] = {v0, v1};
-                z1[aa] = {v2, v3};
             }
-            fft8(z0);
-            fft8(z1);
+            fft8p(P);
 #pragma unroll
-            for (int k = 1; k < 8; ++k) {
-                z0[k] = cmul(z0[k], twr[0][k - 1], twi[0][k - 1]);
-                z1[k] = cmul(z1[k], twr[1][k - 1], twi[1][k - 1]);
-            }
-            // 8 x 16 transpose through the group's swizzled patch
+            for (int k = 1; k < 8; ++k) P[k] = cmul2(P[k], twr[k - 1], twi[k - 1]);
+            // 8 x 16 transpose through the group's swizzled patch; an entry is (re A, re B, im A, im B)
             __syncwarp();
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-                *reinterpret_cast<float4*>(myscr + k * 32 + ((g ^ k) << 2)) =
-                    make_float4(z0[k].r, z0[k].i, z1[k].r, z1[k].i);
+                *reinterpret_cast<ulonglong2*>(myscr + k * 32 + ((g ^ k) << 2)) = make_ulonglong2(P[k].r, P[k].i);
             __syncwarp();
-            cf bb[16], Z[16];
+            cf bb[16];
+            c2 Zp[8];
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
                 const float4 v = *reinterpret_cast<const float4*>(myscr + g * 32 + ((jj ^ g) << 2));
-                bb[2 * jj] = {v.x, v.y};
-                bb[2 * jj + 1] = {v.z, v.w};
+                bb[2 * jj] = {v.x, v.z};
+                bb[2 * jj + 1] = {v.y, v.w};
             }
-            fft16(bb, Z);   // Z[k2] = Zc[g + 8 k2]
+            fft16p(bb, Zp);   // Zp[k] = (Zc[g + 8 (2k)], Zc[g + 8 (2k + 1)])
+            cf Z[16];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                upk(Zp[k].r, Z[2 * k].r, Z[2 * k + 1].r);
+                upk(Zp[k].i, Z[2 * k].i, Z[2 * k + 1].i);
+            }
 
             // conjugate partner: lane (8 - g) & 7 of the same group, index 15 - k2
             // (lane 0 pairs with itself at 16 - k2, so as a source it sends a rotated copy)
@@ -488,25 +522,41 @@ __global__ void __launch_bounds__(NT, 1) dsp_umma_kernel(const __grid_constant__
                 R[jj].i = __shfl_sync(0xffffffffu, si, src_lane);
             }
             float* Lrow = Ls + r * LS_PITCH + (int)((row0 + r) & 3) + m;
-            float s1 = 0.0f, s2 = 0.0f;
             constexpr float LN2 = 0.69314718055994530942f;
+            const f2 eps2 = bc(a.log_eps4), ln2p = bc(LN2), cp = bc(-2.0f * LN2);
+            f2 S1 = bc(0.0f), S2 = bc(0.0f);
 #pragma unroll
-            for (int k2 = 0; k2 < 8; ++k2) {
-                const cf zk = Z[k2], zm = R[7 - k2];                     // R[j - 8] holds index j
-                const cf E = {zk.r + zm.r, zk.i - zm.i};
-                const cf D = {zk.r - zm.r, zk.i + zm.i};
-                const cf O = {D.i, -D.r};
-                const cf Tt = cmul(O, spr[k2], spi[k2]);
-                const cf A = cadd(E, Tt), Bc = csub(E, Tt);
-                const float pa = fmaf(A.r, A.r, fmaf(A.i, A.i, a.log_eps4));
-                const float pb = fmaf(Bc.r, Bc.r, fmaf(Bc.i, Bc.i, a.log_eps4));
-                const float la = fmaf(fast_log2(pa), LN2, -2.0f * LN2);
-                const float lb = fmaf(fast_log2(pb), LN2, -2.0f * LN2);
-                Lrow[(g + 8 * k2) * NF] = la;
-                Lrow[(128 - g - 8 * k2) * NF] = lb;
-                s1 += la + lb;
-                s2 = fmaf(la, la, fmaf(lb, lb, s2));
+            for (int j = 0; j < 4; ++j) {                              // bins k2 = 2j | 2j + 1, split step packed
+                const c2 zk = Zp[j];
+                const c2 zm = {pk(R[7 - 2 * j].r, R[6 - 2 * j].r), pk(R[7 - 2 * j].i, R[6 - 2 * j].i)};   // R[j' - 8] holds index j'
+                const f2 Er = add2(zk.r, zm.r), Ei = sub2(zk.i, zm.i);
+                const f2 Dr = sub2(zk.r, zm.r), Di = add2(zk.i, zm.i);
+                // Tt = (D.i - i D.r) * (spr + i spi)
+                const f2 Ttr = fma2(Di, spr[j], mul2(Dr, spi[j]));
+                const f2 Tti = sub2(mul2(Di, spi[j]), mul2(Dr, spr[j]));
+                const f2 Ar = add2(Er, Ttr), Ai = add2(Ei, Tti), Br = sub2(Er, Ttr), Bi = sub2(Ei, Tti);
+                const f2 pa = fma2(Ar, Ar, fma2(Ai, Ai, eps2));
+                const f2 pb = fma2(Br, Br, fma2(Bi, Bi, eps2));
+                float pa0, pa1, pb0, pb1;
+                upk(pa, pa0, pa1);
+                upk(pb, pb0, pb1);
+                const f2 la = fma2(pk(fast_log2(pa0), fast_log2(pa1)), ln2p, cp);
+                const f2 lb = fma2(pk(fast_log2(pb0), fast_log2(pb1)), ln2p, cp);
+                float la0, la1, lb0, lb1;
+                upk(la, la0, la1);
+                upk(lb, lb0, lb1);
+                Lrow[(g + 16 * j) * NF] = la0;
+                Lrow[(g + 16 * j + 8) * NF] = la1;
+                Lrow[(128 - g - 16 * j) * NF] = lb0;
+                Lrow[(120 - g - 16 * j) * NF] = lb1;
+                S1 = add2(S1, add2(la, lb));
+                S2 = fma2(la, la, fma2(lb, lb, S2));
             }
+            float s1, s1b, s2, s2b;
+            upk(S1, s1, s1b);
+            upk(S2, s2, s2b);
+            s1 += s1b;
+            s2 += s2b;
             if (g == 0) {   // bin 64 pairs with itself: |X[64]|^2 = |Zc[64]|^2
                 const cf zz = Z[8];
                 const float p = fmaf(4.0f * zz.r, zz.r, fmaf(4.0f * zz.i, zz.i, a.log_eps4));

@@ -1,1 +1,3 @@
-EEGX_DSP_VARIANT=7 timeout 300 ncu --set full --clock-control none --import-source on -k regex:dsp_umma -c 1 -o gpurun_out/r2_dsp_umma python bench.py --workload dsp --steps 1 --warmup 3 > gpurun_out/ncu_dsp.log 2>&1; echo rc=$?; tail -3 gpurun_out/ncu_dsp.log
+EEGX_DSP_VARIANT=7 timeout 300 python -m pytest tests/test_dsp_gpu.py -x -q -m gpu 2>&1 | tail -5
+EEGX_DSP_PROF=1 EEGX_DSP_VARIANT=7 timeout 120 python bench.py --workload dsp --steps 3 --warmup 3 2>&1 | grep "prof" | tail -2
+EEGX_DSP_VARIANT=7 timeout 120 python bench.py --workload dsp --steps 20 --warmup 5 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['frac'])"
