@@ -142,6 +142,55 @@ typedef unsigned long long f2;
 __device__ __forceinline__ f2 pk2(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ void upk2(f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 bc2(float x) { return pk2(x, x); }
+
+// ---- packed STFT (PS variant): one instruction works on two independent 8-point FFTs (or two bins) ----
+struct c2 { f2 r, i; };   // two complex values: low halves = FFT (or bin) A, high halves = FFT (or bin) B
+__device__ __forceinline__ c2 cadd(c2 a, c2 b) { return {add2(a.r, b.r), add2(a.i, b.i)}; }
+__device__ __forceinline__ c2 csub(c2 a, c2 b) { return {sub2(a.r, b.r), sub2(a.i, b.i)}; }
+__device__ __forceinline__ c2 cadd_mni(c2 x, c2 a) { return {add2(x.r, a.i), sub2(x.i, a.r)}; }   // x + (-i) a
+__device__ __forceinline__ c2 csub_mni(c2 x, c2 a) { return {sub2(x.r, a.i), add2(x.i, a.r)}; }   // x - (-i) a
+__device__ __forceinline__ c2 cmul2(c2 a, f2 wr, f2 wi) {                                           // a * (wr + i wi)
+    return {sub2(mul2(a.r, wr), mul2(a.i, wi)), fma2(a.r, wi, mul2(a.i, wr))};
+}
+__device__ __forceinline__ void fft8p(c2 (&v)[8]) {
+    const f2 rs = bc2(RSQRT2), nrs = bc2(-RSQRT2);
+    const c2 e0 = cadd(v[0], v[4]), e1 = cadd(v[1], v[5]), e2 = cadd(v[2], v[6]), e3 = cadd(v[3], v[7]);
+    const c2 d0 = csub(v[0], v[4]), d1 = csub(v[1], v[5]), d2 = csub(v[2], v[6]), d3 = csub(v[3], v[7]);
+    const c2 o1 = {mul2(add2(d1.r, d1.i), rs), mul2(sub2(d1.i, d1.r), rs)};      // d1 * W8^1
+    const c2 o3 = {mul2(sub2(d3.i, d3.r), rs), mul2(add2(d3.r, d3.i), nrs)};     // d3 * W8^3
+    const c2 s0 = cadd(e0, e2), s1 = csub(e0, e2), s2 = cadd(e1, e3), s3 = csub(e1, e3);
+    v[0] = cadd(s0, s2); v[4] = csub(s0, s2); v[2] = cadd_mni(s1, s3); v[6] = csub_mni(s1, s3);
+    const c2 t0 = cadd_mni(d0, d2), t1 = csub_mni(d0, d2), t2 = cadd(o1, o3), t3 = csub(o1, o3);
+    v[1] = cadd(t0, t2); v[5] = csub(t0, t2); v[3] = cadd_mni(t1, t3); v[7] = csub_mni(t1, t3);
+}
+// 16-point FFT of c[0..15] returned as pairs out[k] = (X[2k], X[2k + 1]): scalar even / odd split and odd-half
+// twiddles, then the two 8-point FFTs packed
+__device__ __forceinline__ void fft16p(const cf (&c)[16], c2 (&out)[8]) {
+    constexpr float C1 = 0.92387953251128675613f, S1 = 0.38268343236508977173f;  // cos/sin(pi/8)
+    cf e[8], o[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+        e[n] = cadd(c[n], c[n + 8]);
+        o[n] = csub(c[n], c[n + 8]);
+    }
+    o[1] = cmul(o[1], C1, -S1);
+    o[2] = {(o[2].r + o[2].i) * RSQRT2, (o[2].i - o[2].r) * RSQRT2};
+    o[3] = cmul(o[3], S1, -C1);
+    o[4] = mul_neg_i(o[4]);
+    o[5] = cmul(o[5], -S1, -C1);
+    o[6] = {(o[6].i - o[6].r) * RSQRT2, -(o[6].r + o[6].i) * RSQRT2};
+    o[7] = cmul(o[7], -C1, -S1);
+#pragma unroll
+    for (int n = 0; n < 8; ++n) out[n] = {pk2(e[n].r, o[n].r), pk2(e[n].i, o[n].i)};
+    fft8p(out);
+}
+// position of extended sample p inside its aligned group of four: (0, 1, 2, 3) -> (0, 2, 1, 3)
+__device__ __forceinline__ int perm4(int p) { return (p & ~3) | ((p & 1) << 1) | ((p >> 1) & 1); }
+
 __host__ __device__ constexpr int padded32(int o) { return o + 4 * (o >> 5); }   // 4 pad floats per 32: conflict-free 128-bit access
 
 // ---- TMA (1-D bulk copy) + mbarrier helpers ----
@@ -199,9 +248,14 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], unsigned a0, unsigned a1
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-template <int ROWS, int NT, bool PK, bool TC = false>
-__global__ void __launch_bounds__(NT, Cfg<ROWS, NT>::CTAS_PER_SM)
+// PS (scalar FIR only): the STFT runs on packed f32x2 values -- the lane's two 8-point FFTs, the two 8-point
+// halves of its 16-point FFT and neighbouring bins of the split step move through FADD2 / FMUL2 / FFMA2 in
+// lockstep; ys then holds every aligned group of four samples as (t, t+2, t+1, t+3) so that a 128-bit load is
+// already the packed (re | re, im | im) pair.
+template <int ROWS, int NT, bool PK, bool TC = false, bool PS = false, int MINB = 0>
+__global__ void __launch_bounds__(NT, MINB ? MINB : Cfg<ROWS, NT>::CTAS_PER_SM)
 dsp_tuned_kernel(const __grid_constant__ TunedArgs a) {
+    static_assert(!PS || (!PK && !TC), "packed STFT: scalar FIR only");
     static_assert(!PK || (ROWS == 1 && Cfg<ROWS, NT>::NGROUPS * 256 >= padded32(2 * (T / 2 + 64)) && NT >= 64),
                   "packed FIR: one row per tile, pairs must fit the STFT scratch");
     static_assert(!TC || (ROWS == 1 && !PK), "tensor-core FIR: one row per tile");
@@ -403,20 +457,25 @@ dsp_tuned_kernel(const __grid_constant__ TunedArgs a) {
             }
             float* yrow = ys + r * YS_PITCH;
             float4* dsty = reinterpret_cast<float4*>(yrow + 128 + 8 * j);
-            dsty[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            dsty[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            if constexpr (PS) {
+                dsty[0] = make_float4(acc[0], acc[2], acc[1], acc[3]);
+                dsty[1] = make_float4(acc[4], acc[6], acc[5], acc[7]);
+            } else {
+                dsty[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                dsty[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            }
             if (j <= 16) {          // reflect copy on the left: index -t for t in [1, 128]
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const int t = 8 * j + e;
-                    if (t >= 1 && t <= 128) yrow[128 - t] = acc[e];
+                    if (t >= 1 && t <= 128) yrow[PS ? perm4(128 - t) : 128 - t] = acc[e];
                 }
             }
             if (j >= 239) {         // reflect copy on the right: index 2(T-1)-t for t in [T-129, T-2]
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const int t = 8 * j + e;
-                    if (t >= T - 129 && t <= T - 2) yrow[2 * (T - 1) - t + 128] = acc[e];
+                    if (t >= T - 129 && t <= T - 2) yrow[PS ? perm4(2 * (T - 1) - t + 128) : 2 * (T - 1) - t + 128] = acc[e];
                 }
             }
         }
@@ -439,6 +498,113 @@ dsp_tuned_kernel(const __grid_constant__ TunedArgs a) {
             const int m = full ? (task & 7) + 8 * q : 32;
             const float* yseg = ys + r * YS_PITCH + m * 64;  // extended position 64 m
 
+            if constexpr (PS) {
+            // packed constants of this lane (built from the scalar tables; the scalar copies die)
+            f2 winr[4], wini[4], ptwr[7], ptwi[7], pspr[4], pspi[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                winr[i] = pk2(win[4 * i + 0], win[4 * i + 2]);
+                wini[i] = pk2(win[4 * i + 1], win[4 * i + 3]);
+                pspr[i] = pk2(spr[2 * i], spr[2 * i + 1]);
+                pspi[i] = pk2(spi[2 * i], spi[2 * i + 1]);
+            }
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                ptwr[k] = pk2(twr[0][k], twr[1][k]);
+                ptwi[k] = pk2(twi[0][k], twi[1][k]);
+            }
+            c2 P[8];
+#pragma unroll
+            for (int aa = 0; aa < 8; ++aa) {
+                const ulonglong2 u = *reinterpret_cast<const ulonglong2*>(yseg + aa * 32 + 4 * g);
+                if (aa < 4) {
+                    P[aa] = {mul2(u.x, winr[aa]), mul2(u.y, wini[aa])};
+                } else {   // hann[n + 128] = 1 - hann[n]
+                    P[aa] = {sub2(u.x, mul2(u.x, winr[aa - 4])), sub2(u.y, mul2(u.y, wini[aa - 4]))};
+                }
+            }
+            fft8p(P);
+#pragma unroll
+            for (int k = 1; k < 8; ++k) P[k] = cmul2(P[k], ptwr[k - 1], ptwi[k - 1]);
+            // 8 x 16 transpose through the group's swizzled patch; an entry is (re A, re B, im A, im B)
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                *reinterpret_cast<ulonglong2*>(myscr + k * 32 + ((g ^ k) << 2)) = make_ulonglong2(P[k].r, P[k].i);
+            __syncwarp();
+            cf bb[16];
+            c2 Zp[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const float4 v = *reinterpret_cast<const float4*>(myscr + g * 32 + ((jj ^ g) << 2));
+                bb[2 * jj] = {v.x, v.z};
+                bb[2 * jj + 1] = {v.y, v.w};
+            }
+            fft16p(bb, Zp);   // Zp[k] = (Zc[g + 8 (2k)], Zc[g + 8 (2k + 1)])
+            cf Z[16];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                upk2(Zp[k].r, Z[2 * k].r, Z[2 * k + 1].r);
+                upk2(Zp[k].i, Z[2 * k].i, Z[2 * k + 1].i);
+            }
+            const int src_lane = (lane & 24) | ((8 - g) & 7);
+            cf R[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const cf own = Z[8 + jj];
+                const cf rot = Z[(9 + jj) & 15];
+                const float sr = g == 0 ? rot.r : own.r;
+                const float si = g == 0 ? rot.i : own.i;
+                R[jj].r = __shfl_sync(0xffffffffu, sr, src_lane);
+                R[jj].i = __shfl_sync(0xffffffffu, si, src_lane);
+            }
+            float* Lrow = Ls + r * LS_PITCH + (int)((row0 + r) & 3) + m;
+            constexpr float LN2 = 0.69314718055994530942f;
+            if (valid) {
+                const f2 eps2 = bc2(a.log_eps4), ln2p = bc2(LN2), cp = bc2(-2.0f * LN2);
+                f2 S1 = bc2(0.0f), S2 = bc2(0.0f);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {                          // bins k2 = 2j | 2j + 1, split step packed
+                    const c2 zk = Zp[j];
+                    const c2 zm = {pk2(R[7 - 2 * j].r, R[6 - 2 * j].r), pk2(R[7 - 2 * j].i, R[6 - 2 * j].i)};
+                    const f2 Er = add2(zk.r, zm.r), Ei = sub2(zk.i, zm.i);
+                    const f2 Dr = sub2(zk.r, zm.r), Di = add2(zk.i, zm.i);
+                    const f2 Ttr = fma2(Di, pspr[j], mul2(Dr, pspi[j]));         // Tt = (D.i - i D.r) * (spr + i spi)
+                    const f2 Tti = sub2(mul2(Di, pspi[j]), mul2(Dr, pspr[j]));
+                    const f2 Ar = add2(Er, Ttr), Ai = add2(Ei, Tti), Br = sub2(Er, Ttr), Bi = sub2(Ei, Tti);
+                    const f2 pa = fma2(Ar, Ar, fma2(Ai, Ai, eps2));
+                    const f2 pb = fma2(Br, Br, fma2(Bi, Bi, eps2));
+                    float pa0, pa1, pb0, pb1;
+                    upk2(pa, pa0, pa1);
+                    upk2(pb, pb0, pb1);
+                    const f2 la = fma2(pk2(fast_log2(pa0), fast_log2(pa1)), ln2p, cp);
+                    const f2 lb = fma2(pk2(fast_log2(pb0), fast_log2(pb1)), ln2p, cp);
+                    float la0, la1, lb0, lb1;
+                    upk2(la, la0, la1);
+                    upk2(lb, lb0, lb1);
+                    Lrow[(g + 16 * j) * NF] = la0;
+                    Lrow[(g + 16 * j + 8) * NF] = la1;
+                    Lrow[(128 - g - 16 * j) * NF] = lb0;
+                    Lrow[(120 - g - 16 * j) * NF] = lb1;
+                    S1 = add2(S1, add2(la, lb));
+                    S2 = fma2(la, la, fma2(lb, lb, S2));
+                }
+                float s1, s1b, s2, s2b;
+                upk2(S1, s1, s1b);
+                upk2(S2, s2, s2b);
+                s1 += s1b;
+                s2 += s2b;
+                if (g == 0) {   // bin 64 pairs with itself: |X[64]|^2 = |Zc[64]|^2
+                    const cf zz = Z[8];
+                    const float p = fmaf(4.0f * zz.r, zz.r, fmaf(4.0f * zz.i, zz.i, a.log_eps4));
+                    const float l = fmaf(fast_log2(p), LN2, -2.0f * LN2);
+                    Lrow[64 * NF] = l;
+                    s1 += l;
+                    s2 = fmaf(l, l, s2);
+                }
+                stat[(r * NF + m) * 8 + g] = make_float2(s1, s2);
+            }
+            } else {
             cf z0[8], z1[8];
 #pragma unroll
             for (int aa = 0; aa < 8; ++aa) {
@@ -521,6 +687,7 @@ dsp_tuned_kernel(const __grid_constant__ TunedArgs a) {
                 }
                 stat[(r * NF + m) * 8 + g] = make_float2(s1, s2);
             }
+            }   // !PS
         }
         __syncthreads();
 
@@ -603,15 +770,15 @@ bool dsp_tuned_supported(const eegx_dsp_plan* p) {
 int dsp_tuned_table_floats() { return 8 * LANE_TABLE; }
 void dsp_tuned_fill_tables(float* host) { fill_lane_tables(host); }
 
-template <int ROWS, int NT, bool PK = false, bool TC = false>
+template <int ROWS, int NT, bool PK = false, bool TC = false, bool PS = false, int MINB = 0>
 int launch_variant(const TunedArgs& a, cudaStream_t st) {
     using C = Cfg<ROWS, NT>;
-    EEGX_CUDA_CHECK(cudaFuncSetAttribute(dsp_tuned_kernel<ROWS, NT, PK, TC>,
+    EEGX_CUDA_CHECK(cudaFuncSetAttribute(dsp_tuned_kernel<ROWS, NT, PK, TC, PS, MINB>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
     const long long ntiles = (a.rows + ROWS - 1) / ROWS;
-    const long long max_ctas = (long long)C::CTAS_PER_SM * kNumSMsB200;
+    const long long max_ctas = (long long)(MINB ? MINB : C::CTAS_PER_SM) * kNumSMsB200;
     const int grid = (int)(ntiles < max_ctas ? ntiles : max_ctas);
-    dsp_tuned_kernel<ROWS, NT, PK, TC><<<grid, NT, C::SMEM_BYTES, st>>>(a);
+    dsp_tuned_kernel<ROWS, NT, PK, TC, PS, MINB><<<grid, NT, C::SMEM_BYTES, st>>>(a);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
 }
@@ -632,6 +799,9 @@ int launch_dsp_tuned(const eegx_dsp_plan* plan, const DspArgs& d, cudaStream_t s
         case 4: return launch_variant<1, 96, true>(a, st);   // 1 row per tile, packed half-row FIR
         case 5: return launch_variant<1, 96, false, true>(a, st);    // 1 row per tile, FIR as 3xTF32 Toeplitz MMAs
         case 6: return launch_variant<1, 128, false, true>(a, st);   // same, 4 warps (16 FIR blocks divide evenly)
+        case 8: return launch_variant<1, 96, false, false, true>(a, st);   // scalar FIR + packed f32x2 STFT
+        case 9: return launch_variant<1, 128, false, false, true, 4>(a, st);  // same, 4 warps x 4 CTAs/SM (128 registers)
+        case 10: return launch_variant<1, 96, false, false, true, 5>(a, st);  // same, 3 warps x 5 CTAs/SM (136 registers)
         case 7: return launch_dsp_umma(plan, d, st);    // FIR as tcgen05 kind::tf32 Toeplitz MMAs, operands in tensor memory (dsp_umma.cu)
         case 1: return launch_variant<1, 96>(a, st);    // 4 CTAs/SM x 3 warps, 1 row per tile
         case 2: return launch_variant<2, 192>(a, st);   // 2 CTAs/SM x 6 warps, 2 rows per tile
