@@ -475,13 +475,16 @@ def run_ours(args, rank, world, local_rank):
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
-    def stage(i):
+    def stage_from(i, src):
         k = i % 2
         copy_stream.wait_event(consumed[k])                 # the step that read this staging set has finished
         with torch.cuda.stream(copy_stream):
-            for n, t in host[k].items():
-                dev_stage[k][n].copy_(t, non_blocking=True)
+            for n in dev_stage[k]:
+                dev_stage[k][n].copy_(src[n], non_blocking=True)
             ready[k].record(copy_stream)
+
+    def stage(i):
+        stage_from(i, host[i % 2])
 
     def e2e_steps(n):
         cur = torch.cuda.current_stream()
@@ -509,6 +512,12 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = float(te.item()) / args.steps
     h2d = 4 * B_PER_GPU * C * T + 2 * 8 * B_PER_GPU * L_TOK
+
+    # ---------------- the same, with the batches coming out of the data path (row f2): memory-mapped trial store
+    # -> threaded gather into pinned staging -> tokens -> PrefetchLoader -> H2D -> step -> D2H loss ----------------
+    e2e_loader = None
+    if world == 1 and not args.no_loader_arm:
+        e2e_loader = time_loader_e2e(step, stage_from, ready, consumed, dev_stage, loss_host, min(args.steps, 12), dev)
 
     # ---------------- dominant kernel: per-launch GEMM timing pass (eager, outside the graph) ----------------
     # (single stream, so the events bracket exactly one GEMM and nothing runs beside it)
@@ -565,6 +574,7 @@ def run_ours(args, rank, world, local_rank):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "path": "pinned host batch -> H2D (copy stream, one batch ahead) -> EEGTrainer.train_step + "
                             "optimizer step -> D2H loss"},
+            "e2e_loader": e2e_loader,
             "gpu_launches": launches,
             "gpu_launches_note": f"libeegx entry-point calls (each enqueues 1-3 of our kernels): {graph_calls} per "
                                  f"step replayed inside the CUDA graph (DSP, tcgen05 GEMMs, fused norm/activation/"
@@ -573,19 +583,104 @@ def run_ours(args, rank, world, local_rank):
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
                          "frac": achieved / tf_peak, "traffic": None, "peak_source": src,
                          "kernel": "gemm_bf16_kernel (tcgen05)", "kernel_ms_per_step": gemm_ms,
-                         "launches_per_step": len(rec), "algorithmic_flops_per_step": gemm_flops,
+                         "launches_per_step": len(rec), "launched_flops_per_step": gemm_flops,
+                         "flops_note": "sum of 2*M*N*K over the launched GEMMs; the conv-as-GEMM launches include "
+                                       "the zero guard rows of the channels-last layout (about 2 % of the total)",
                          "event_pair_overhead_ms_removed": ev_overhead_ms,
                          "method": "CUDA events around every GEMM launch of one single-stream eager step (GPU held "
                                    "behind the CPU so host work never falls between the events), empty-pair "
                                    "overhead calibrated and subtracted",
                          "share_of_step": gemm_ms / ms_per_step,
-                         "share_note": "GEMM kernel time / wall time of the step; the step packs ~41 ms of kernel time "
-                                       "(ncu launch list, profiles/r1_train_launch_shares.txt: GEMMs 44 % of it) into "
-                                       "~30 ms of wall time on 4 region streams, so the two shares differ by that factor "
-                                       "while the GEMM milliseconds agree"},
+                         "share_note": "GEMM kernel time of a single-stream step / wall time of the graph-replayed "
+                                       "step; the replayed step packs ~31 ms of serialised kernel time (ncu launch "
+                                       "list, profiles/r2_train_launch_shares.txt: GEMMs 50 % of it) into the wall "
+                                       "time on a main stream plus a weight-gradient side stream"},
             "dsp": dsp,
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         }), flush=True)
+
+
+def time_loader_e2e(step, stage_from, ready, consumed, dev_stage, loss_host, steps, dev):
+    """End to end through the data path a user drives: a synthetic pickle set of the bench
+    shape -> `EEGDataset.build_trial_store` -> `PrefetchLoader` (background thread: memory-mapped gather into pinned
+    staging + tokenisation, two batches ahead) -> H2D on the copy stream -> train step -> D2H loss.  Timed with CUDA
+    events over `steps` steps after 2 warm-up steps; the host gather rate is reported beside it."""
+    import pickle
+    import shutil
+    import tempfile
+    from transformers import BertTokenizer
+    import imagined_speech_translation_b200 as pkg
+    fix = os.path.join(ROOT, "tests", "golden", "dataset")
+    d = tempfile.mkdtemp(prefix="eegx_bench_")
+    try:
+        import pandas as pd
+        labels = list(pd.read_csv(os.path.join(fix, "montage.csv"))["label"].to_numpy()[:C])
+        labels += [f"AUX{i}" for i in range(C - len(labels))]      # configs[3] has more channels than the montage names
+        pd.DataFrame({"label": labels}).to_csv(os.path.join(d, "montage.csv"), index=False)
+        rng = np.random.default_rng(7)
+        words = ["数据", "样本", "想象", "语音", "脑电", "翻译"]
+        n_files, per_file = 4, B_PER_GPU // 2                   # 2 x B trials: two batches per epoch
+        os.mkdir(os.path.join(d, "runs"))
+        for f in range(n_files):
+            run = [{"input_features": rng.normal(0, 20, (1, C, T)).astype(np.float32),
+                    "text": " ".join(rng.choice(words, 3))} for _ in range(per_file)]
+            with open(os.path.join(d, "runs", f"run{f}.pkl"), "wb") as fh:
+                pickle.dump(run, fh)
+        tok = BertTokenizer(os.path.join(fix, "vocab.txt"), bos_token="[CLS]", eos_token="[SEP]")
+        ds = pkg.EEGDataset(os.path.join(d, "runs"), os.path.join(d, "montage.csv"), tok, max_length=L_TOK,
+                            data_augmentation=False, device=str(dev))
+        ds.build_trial_store(os.path.join(d, "trials.eegx"))
+        ds._load_file.cache_clear()
+        loader = pkg.PrefetchLoader(ds, B_PER_GPU, shuffle=True, drop_last=True, seed=1, depth=2)
+
+        def batches():
+            epoch = 0
+            while True:
+                loader.set_epoch(epoch)
+                for b in loader:
+                    yield b
+                epoch += 1
+
+        def run_steps(it, n):
+            cur = torch.cuda.current_stream()
+            consumed[0].record(cur)
+            consumed[1].record(cur)
+            stage_from(0, next(it))
+            for i in range(n):
+                k = i % 2
+                cur.wait_event(ready[k])
+                if i + 1 < n:
+                    stage_from(i + 1, next(it))                 # next batch: host gather done ahead, H2D overlaps the step
+                l = step(dev_stage[k])
+                consumed[k].record(cur)
+                loss_host[i % loss_host.numel()].copy_(l, non_blocking=True)
+
+        it = batches()
+        run_steps(it, 2)
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        t0.record()
+        run_steps(it, steps)
+        t1.record()
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - w0) * 1e3 / steps
+        ms = t0.elapsed_time(t1) / steps
+        it.close()
+        # host side alone: gather + tokens for one batch
+        order = np.arange(len(ds))
+        ds.fetch(order[:B_PER_GPU])
+        h0 = time.perf_counter()
+        for r in range(4):
+            ds.fetch(order[(r % 2) * B_PER_GPU:(r % 2 + 1) * B_PER_GPU])
+        host_rate = 4 * B_PER_GPU / (time.perf_counter() - h0)
+        return {"value": B_PER_GPU / (ms / 1000.0), "unit": UNIT, "ms_per_step": ms, "wall_ms_per_step": wall_ms,
+                "steps": steps, "host_fetch_trials_per_s": host_rate, "store_trials": len(ds),
+                "path": "synthetic pickles -> EEGDataset.build_trial_store -> PrefetchLoader (background thread: "
+                        "memory-mapped gather into pinned staging + BertTokenizer, depth 2) -> H2D (copy stream) -> "
+                        "EEGTrainer.train_step + optimizer step -> D2H loss"}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
 
 
 def main():
@@ -599,6 +694,7 @@ def main():
                     help="stft = BASELINE configs[2] (default, the configuration the metric is quoted on); "
                          "long = configs[3] (128 ch x 4096 samples, n_fft 1024 / hop 256)")
     ap.add_argument("--no-torch-arm", action="store_true", help="skip the stock-PyTorch-on-B200 comparator")
+    ap.add_argument("--no-loader-arm", action="store_true", help="skip the TrialStore + PrefetchLoader end-to-end leg")
     args = ap.parse_args()
     select_config(args.config)
     if args.impl == "ours":

@@ -186,15 +186,19 @@ class Conv1DWithAttention(nn.Module):
         self.diversity_head = nn.Linear(hidden_dim, hidden_dim)
 
     # ------------------------------------------------------------------ CNN stack
-    def _res_block(self, hg, conv, bn, res, drop, B, T):
+    def _res_block(self, hg, conv, bn, res, drop, B, T, cin_pad=0):
         """gelu(bn(conv(h)) + res(h)) -> dropout -> zeroed padding rows, on guarded channels-last rows
-        (reference layers.py:142-174): two GEMMs, two statistics reductions, one fused apply."""
+        (reference layers.py:142-174): two GEMMs, two statistics reductions, one fused apply.
+        cin_pad: zero input channels appended to the block's input (first block only, see _cnn); the weights get
+        matching zero columns through F.pad, so their gradients flow back to the unpadded parameters."""
         M = B * (T + 2 * PAD)
-        ya = nn_ops.conv_g(hg, conv.weight, conv.bias, M, bias_grad=not bn.training)
+        w = F.pad(conv.weight, (0, 0, 0, cin_pad)) if cin_pad else conv.weight
+        ya = nn_ops.conv_g(hg, w, conv.bias, M, bias_grad=not bn.training)
         p = drop.p if drop is not None else 0.0
         if isinstance(res, nn.Identity):
             return fused.bn_act(ya, bn, hg, None, B, T, p=p, training=bn.training, drop_training=self.training)
-        yr = nn_ops.conv_g(hg, res[0].weight, None, M)
+        wr = F.pad(res[0].weight, (0, 0, 0, cin_pad)) if cin_pad else res[0].weight
+        yr = nn_ops.conv_g(hg, wr, None, M)
         return fused.bn_act(ya, bn, yr, res[1], B, T, p=p, training=bn.training, drop_training=self.training)
 
     def _depthwise_block(self, hg, B, T):
@@ -208,10 +212,14 @@ class Conv1DWithAttention(nn.Module):
 
     def _cnn(self, x):
         B, C, T = x.shape
-        if C % 8 != 0:
-            raise ValueError("n_channels must be a multiple of 8 on this path (TMA row pitch)")
+        # the TMA row pitch of the channels-last rows is 16 bytes = 8 bf16 channels: a region whose channel count is
+        # not a multiple of 8 (the reference montage gives 16 / 9 / 11 / 12) gets zero channels appended, with zero
+        # weight columns against them -- the products are exact zeros, the result is unchanged
+        cin_pad = (-C) % 8
+        if cin_pad:
+            x = F.pad(x, (0, 0, 0, cin_pad))
         hg = fused.to_rows(x.float())                           # guarded channels-last bf16 rows
-        hg = self._res_block(hg, self.conv1, self.bn1, self.residual1, self.dropout_light, B, T)
+        hg = self._res_block(hg, self.conv1, self.bn1, self.residual1, self.dropout_light, B, T, cin_pad=cin_pad)
         hg = self._res_block(hg, self.conv2, self.bn2, self.residual2, self.dropout_light, B, T)
         hg = self._depthwise_block(hg, B, T)
         hg = self._res_block(hg, self.conv3, self.bn3, self.residual3, self.dropout_medium, B, T)

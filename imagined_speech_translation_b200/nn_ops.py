@@ -26,6 +26,9 @@ def _cached(param: torch.Tensor, tag: str, make):
     version counter moves (i.e. after an optimizer step).  The entry keeps the base tensor alive,
     so its id() cannot be recycled while the entry exists."""
     base = param._base if param._base is not None else param
+    if not isinstance(base, torch.nn.Parameter):       # a computed tensor (e.g. a zero-padded weight): nothing to key on
+        with torch.no_grad():
+            return make(param.detach())
     key = (id(base), param.storage_offset(), tuple(param.shape), tag)
     hit = _pack_cache.get(key)
     ver = base._version

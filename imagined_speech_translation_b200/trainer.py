@@ -92,7 +92,7 @@ def initialize_custom_weights(model):
 
 class EEGTrainer:
     def __init__(self, model, tokenizer, train_loader, val_loader, optimizer, scheduler, config,
-                 front_end=None, region_channel_counts=None, process_group=None):
+                 front_end=None, region_channel_counts=None, process_group=None, normalizer=None):
         self.model = model
         self.tokenizer = tokenizer
         self.train_loader = train_loader
@@ -102,6 +102,10 @@ class EEGTrainer:
         self.config = config
         self.device = next(model.parameters()).device
         self.front_end = front_end                      # SpectrogramFrontEnd: batch['raw'] -> regions
+        # RegionNormalizer (the reference's own preprocessing, dataset.py:172-225: gather the four regions,
+        # nan_to_num, RobustScaler / z-score fallback) for batch['raw'] when no spectrogram front-end is given;
+        # taken from the train loader's dataset when that is a data.EEGDataset
+        self.normalizer = normalizer
         self.region_channel_counts = region_channel_counts
         self.process_group = process_group
         self.world_size = torch.distributed.get_world_size(process_group) \
@@ -124,6 +128,17 @@ class EEGTrainer:
         if 'raw' in batch and self.front_end is not None:
             raw = batch['raw'].to(self.device, non_blocking=True)
             return self.front_end.split_regions(self.front_end(raw), self.region_channel_counts)
+        if 'raw' in batch:
+            # reference-actual path (rows a1/a2): the arithmetic the reference does per item in __getitem__ runs
+            # here, once per batch, on the GPU
+            norm = self.normalizer
+            if norm is None:
+                ds = getattr(self.train_loader, 'dataset', None)
+                if ds is None or not hasattr(ds, 'normalizer'):
+                    raise ValueError("batch carries 'raw' trials but the trainer has neither a front_end nor a "
+                                     "normalizer (pass normalizer=RegionNormalizer(...) or a data.EEGDataset loader)")
+                norm = self.normalizer = ds.normalizer()
+            return norm(batch['raw'].to(self.device, non_blocking=True).float())
         return [r.to(self.device, non_blocking=True) for r in batch['eeg']]
 
     def forward_pass(self, eeg, decoder_input_ids, labels):

@@ -114,3 +114,33 @@ def test_rejects_cpu_tensors():
     m = Conv1DWithAttention(16, 33, hidden_dim=768)
     with pytest.raises(RuntimeError):
         m(torch.zeros(2, 16, 33))
+
+
+@pytest.mark.parametrize("n_channels", [9, 11, 12])
+def test_region_sizes_of_the_reference_montage(n_channels):
+    """The reference montage gives regions of 16 / 9 / 11 / 12 channels (dataset.py region map): channel counts
+    that are not a multiple of 8 run through zero-padded channels.  Checked against the CPU oracle on the same
+    weights: features, input gradient, and the gradient of the padded conv1 / residual1 weights."""
+    from oracle import encoder_oracle as eo      # checker only
+    T, B = 33, 4
+    m = Conv1DWithAttention(n_channels, T, hidden_dim=768)
+    fill_params(m, seed=5)
+    zero_dropout(m)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x = make_input((B, n_channels, T), seed=6)
+    gout = make_input((B, 768), seed=7)
+    xr = x.clone().requires_grad_(True)
+    params = {k: sd[k].clone().requires_grad_(True) for k, _ in m.named_parameters()}
+    ref = eo.region_encoder({**sd, **params}, xr, train=True)
+    (ref * gout).sum().backward()
+    m = m.cuda().train()
+    xg = x.cuda().requires_grad_(True)
+    out = m(xg)
+    (out * gout.cuda()).sum().backward()
+    assert out.shape == ref.shape
+    assert _cos(out.detach().cpu(), ref.detach()) >= 0.999
+    assert _cos(xg.grad.cpu(), xr.grad) >= 0.99
+    for name in ("conv1.weight", "residual1.0.weight"):
+        g = dict(m.named_parameters())[name].grad
+        assert g is not None and g.shape == sd[name].shape
+        assert _cos(g.cpu(), params[name].grad) >= 0.99, name

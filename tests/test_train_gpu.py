@@ -338,3 +338,36 @@ def test_evaluate_reports_loss_and_generated_text():
         direct = model.generate(eeg_data=[r.cuda() for r in batches[0]["eeg"]], **cfg["generation"]["eval"]).cpu()
     want = [tok.decode(direct[i], skip_special_tokens=True, clean_up_tokenization_spaces=True).strip() for i in range(4)]
     assert trainer.last_predictions[:4] == want
+
+
+def test_raw_batches_take_the_reference_normalisation_path():
+    """Row a2 reachable from the step: a batch carrying 'raw' trials and no spectrogram front-end goes through the
+    RegionNormalizer (dataset.py:172-225 on the GPU) and yields the same loss as the pre-normalised 'eeg' list."""
+    from imagined_speech_translation_b200.preprocess import RegionNormalizer, REGION_ORDER
+    g = torch.Generator().manual_seed(3)
+    C_in, T, B = 24, 37, 2
+    region_indices = {n: list(range(1 + 5 * i, 1 + 5 * i + 4)) for i, n in enumerate(REGION_ORDER)}
+    centers = {n: torch.randn(4, generator=g).numpy() for n in REGION_ORDER[:3]}        # 4th region: z-score fallback
+    scales = {n: (1.0 + torch.rand(4, generator=g)).numpy() for n in REGION_ORDER[:3]}
+    norm = RegionNormalizer(region_indices, centers, scales)
+    counts = {n: 4 for n in REGION_ORDER}
+    torch.manual_seed(0)
+    model = EEGDecodingModel(n_timepoints=T, region_channel_counts=counts).cuda().eval()
+    cfg = dict(tr.CONFIG, accumulation_steps=1)
+    opt = tr.build_optimizer(model, cfg)
+    t = tr.EEGTrainer(model, None, None, None, opt, tr.cosine_schedule_with_warmup(opt, 1, 10), cfg, normalizer=norm)
+    raw = 30.0 * torch.randn(B, C_in, T, generator=g)
+    raw[0, 2, 5] = float('nan')
+    labels = torch.randint(1, 51271, (B, 8), generator=g)
+    ids = torch.cat([torch.full((B, 1), 101), labels[:, :-1]], 1)
+    batch = {'raw': raw, 'decoder_input_ids': ids, 'labels': labels}
+    regions = t._regions(batch)
+    assert [tuple(r.shape) for r in regions] == [(B, 4, T)] * 4 and all(torch.isfinite(r).all() for r in regions)
+    with torch.no_grad():
+        a = t.forward_pass(regions, ids.cuda(), labels.cuda()).loss
+        b = t.forward_pass(t._regions({'eeg': [r.cpu() for r in regions]}), ids.cuda(), labels.cuda()).loss
+    assert torch.equal(a, b)
+    # no front-end, no normalizer, no dataset to take one from: a loud error, not a silent pass-through
+    t2 = tr.EEGTrainer(model, None, None, None, opt, tr.cosine_schedule_with_warmup(opt, 1, 10), cfg)
+    with pytest.raises(ValueError):
+        t2._regions(batch)
