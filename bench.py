@@ -546,6 +546,15 @@ def run_ours(args, rank, world, local_rank):
     ev_overhead_ms = float(np.median([a_.elapsed_time(b_) for a_, b_ in pairs]))
     gemm_ms = sum(max(r[0].elapsed_time(r[1]) - ev_overhead_ms, 0.0) for r in rec)
     gemm_flops = sum(r[2] for r in rec)
+    # operand + result bytes of the launched GEMMs (bf16 operands, bf16 or fp32 results)
+    gemm_bytes = sum(b_ * ((m_ * k_ + n_ * k_) * 2 + m_ * n_ * esz_) for _, _, _, (b_, m_, n_, k_, _, _, esz_) in rec)
+    gemm_traffic = None
+    try:
+        if CONFIG_NAME == "stft":
+            with open(os.path.join(ROOT, "profiles", "gemm_traffic.json")) as fh:
+                gemm_traffic = json.load(fh).get("dram_bytes_per_launch")
+    except Exception:
+        pass
 
     dsp = bench_dsp(fe, dev, rank, world, args, barrier)
     if world > 1:
@@ -585,7 +594,10 @@ def run_ours(args, rank, world, local_rank):
                                  f"attention kernels) + {eager_calls // max(args.steps, 1)} per step for clip + AdamW; "
                                  "BART decoder internals and small reshapes still run as torch kernels",
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
-                         "frac": achieved / tf_peak, "traffic": None, "peak_source": src,
+                         "frac": achieved / tf_peak, "traffic": gemm_traffic,
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum averaged over the GEMM launches "
+                                         "of one step (profiles/gemm_traffic.json, one ncu pass of this command)",
+                         "algorithmic_bytes_per_launch": gemm_bytes / max(len(rec), 1), "peak_source": src,
                          "kernel": "gemm_bf16_kernel (tcgen05)", "kernel_ms_per_step": gemm_ms,
                          "launches_per_step": len(rec), "launched_flops_per_step": gemm_flops,
                          "flops_note": "sum of 2*M*N*K over the launched GEMMs; the conv-as-GEMM launches include "

@@ -108,5 +108,5 @@ def gemm(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     if GEMM_TIMING is not None:
         e1.record()
         GEMM_TIMING.append((e0, e1, 2.0 * M * N * K * batch * groups,
-                            (batch * groups, M, N, K, int(a_mn_major), int(b_mn_major))))
+                            (batch * groups, M, N, K, int(a_mn_major), int(b_mn_major), out.element_size())))
     return out

@@ -78,3 +78,69 @@ def test_fused_decoder_matches_transformers():
     for n in grads_r:
         assert _cos(grads_f[n], grads_r[n]) >= 0.99, n
         assert abs(grads_f[n].norm().item() / grads_r[n].norm().item() - 1) <= 0.05, n
+
+
+def test_fused_decoder_matches_transformers_on_trained_weights():
+    """At random init every logit is near zero and loss ~ ln V whatever the arithmetic: the loss bound of the test
+    above says little.  Here the stock fp32 path first fits a fixed batch for 150 AdamW steps (loss falls from
+    ~10.8 to well below 3), so logits are large and structured; then the fused bf16 path is compared on those
+    weights: loss, logits, the argmax tokens and the gradients."""
+    torch.manual_seed(0)
+    dec = BARTDecoder(768).cuda().train()
+    for m in dec.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    for layer in dec.bart.model.decoder.layers:
+        layer.dropout = 0.0
+    dec.bart.model.decoder.dropout = 0.0
+    B, L = 8, 16
+    g = torch.Generator(device="cuda").manual_seed(2)
+    feat = torch.randn(B, 768, device="cuda", generator=g)
+    labels = torch.randint(1, 51271, (B, L), device="cuda", generator=g)
+    labels[:, 12:] = -100
+    ids = torch.cat([torch.full((B, 1), 101, device="cuda"), labels[:, :-1].clamp_min(0)], 1)
+    dec.fused_decoder, dec.autocast_dtype = False, None                      # stock transformers, fp32
+    opt = torch.optim.AdamW([p for n, p in dec.named_parameters() if ".encoder." not in n], lr=1e-4, weight_decay=0.0)
+    first = None
+    for _ in range(150):
+        opt.zero_grad(set_to_none=True)
+        loss = dec(feat, decoder_input_ids=ids, labels=labels).loss
+        first = loss.item() if first is None else first
+        loss.backward()
+        opt.step()
+    nn_ops.clear_pack_cache()
+
+    # gradients are compared on a second, unseen batch: at the fitted minimum they are ~1e-7 and pure rounding noise
+    labels2 = torch.randint(1, 51271, (B, L), device="cuda", generator=g)
+    labels2[:, 10:] = -100
+    ids2 = torch.cat([torch.full((B, 1), 101, device="cuda"), labels2[:, :-1].clamp_min(0)], 1)
+    feat2 = torch.randn(B, 768, device="cuda", generator=g)
+
+    def run(fused_path, ft, di, lb):
+        dec.zero_grad(set_to_none=True)
+        dec.fused_decoder = fused_path
+        dec.autocast_dtype = torch.bfloat16 if fused_path else None
+        f = ft.clone().requires_grad_(True)
+        out = dec(f, decoder_input_ids=di, labels=lb)
+        out.loss.backward()
+        params = dict(dec.named_parameters())
+        names = ["eeg_to_bart.0.weight", "bart.model.decoder.layers.0.self_attn.q_proj.weight",
+                 "bart.model.decoder.layers.5.fc1.weight", "bart.model.decoder.layers.3.final_layer_norm.weight"]
+        return out.loss.item(), out.logits.detach().float().clone(), f.grad.clone(), \
+            {n: params[n].grad.detach().float().clone() for n in names}
+
+    loss_r, logits_r, _, _ = run(False, feat, ids, labels)
+    loss_f, logits_f, _, _ = run(True, feat, ids, labels)
+    assert first > 10.0 and loss_r < 3.0, (first, loss_r)                    # the batch was really fitted
+    assert abs(loss_f - loss_r) <= 3e-2 * max(1.0, loss_r), (loss_f, loss_r)
+    assert ((logits_f - logits_r).abs().max() / logits_r.abs().max()).item() <= 5e-2
+    valid = labels != -100
+    agree = (logits_f.argmax(-1) == logits_r.argmax(-1))[valid].float().mean().item()
+    assert agree >= 0.98, agree
+    loss2_r, logits2_r, dfeat_r, grads_r = run(False, feat2, ids2, labels2)
+    loss2_f, logits2_f, dfeat_f, grads_f = run(True, feat2, ids2, labels2)
+    assert abs(loss2_f - loss2_r) <= 3e-2 * max(1.0, loss2_r), (loss2_f, loss2_r)
+    assert ((logits2_f - logits2_r).abs().max() / logits2_r.abs().max()).item() <= 5e-2
+    assert _cos(dfeat_f, dfeat_r) >= 0.99
+    for n in grads_r:
+        assert _cos(grads_f[n], grads_r[n]) >= 0.98, n

@@ -35,6 +35,6 @@ for e0, e1, fl, shp in rec:
     a = agg[shp]; a[0] += 1; a[1] += e0.elapsed_time(e1); a[2] += fl
 tot = sum(a[1] for a in agg.values())
 print(f"{len(rec)} GEMM launches, {tot:.2f} ms (raw event time), {sum(a[2] for a in agg.values()) / tot / 1e9:.0f} TF/s")
-print(f"{'batch,M,N,K,aT,bT':>34} {'n':>4} {'ms':>7} {'us/call':>8} {'TF/s':>7}")
+print(f"{'batch,M,N,K,aT,bT,out bytes':>34} {'n':>4} {'ms':>7} {'us/call':>8} {'TF/s':>7}")
 for shp, (n, ms, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
     print(f"{str(shp):>34} {n:4d} {ms:7.3f} {1e3 * ms / n:8.1f} {fl / ms / 1e9:7.0f}")
