@@ -1,2 +1,1 @@
-timeout 600 python -m pytest tests/test_decoder_gpu.py -x -q -m gpu -k trained 2>&1 | grep -v Warning | tail -12
-EEGX_NCU_STEP=1 timeout 500 ncu --profile-from-start off -k regex:gemm --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/r2_gemm_dram.csv python bench.py --steps 2 --warmup 3 --no-torch-arm --no-loader-arm > gpurun_out/ncu_gemm.log 2>&1; echo "ncu rc=$?"
+timeout 600 python -m pytest tests/test_train_gpu.py tests/test_decoder_gpu.py -x -q -m gpu -k "two_gpus or trained" 2>&1 | grep -v Warning | tail -6 | tee gpurun_out/r2_two_gpu_tests.txt
