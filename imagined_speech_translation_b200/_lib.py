@@ -106,6 +106,8 @@ SIGNATURES.update({
     "eegx_augment_f32": (_I, [_P, _P, _I64, _I64, _I64, _P, _P, _P, _P, _U32, _P]),
     "eegx_wake_dense_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I]),
     "eegx_wake_dense_f64": (_I, [_P] * 6 + [_I64, _I64, _I64, _I64, C.c_double, _I, _I, _P, _P, _P, _P, _SZ, _P]),
+    "eegx_wake_conv2d_f64": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64, _P, C.c_double, _P, _P, _P]),
+    "eegx_wake_maxpool_f64": (_I, [_P, _I64, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P]),
     "eegx_logsoftmax_topk_f32": (_I, [_P, _I64, _I64, _I64, C.c_int32, _I64, _P, _P, _P]),
     "eegx_ce_fwd_bf16": (_I, [_P, _I64, _P, _I64, _I64, _I64, _P, _P, _P]),
     "eegx_ce_bwd_bf16": (_I, [_P, _I64, _P, _P, _P, _P, _I64, _I64, _I64, _P]),

@@ -252,7 +252,11 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], unsigned a0, unsigned a1
 // halves of its 16-point FFT and neighbouring bins of the split step move through FADD2 / FMUL2 / FFMA2 in
 // lockstep; ys then holds every aligned group of four samples as (t, t+2, t+1, t+3) so that a 128-bit load is
 // already the packed (re | re, im | im) pair.
-template <int ROWS, int NT, bool PK, bool TC = false, bool PS = false, int MINB = 0>
+// BS: bulk store.  Every warp normalises its share of the row IN PLACE in shared memory and hands it to the TMA
+// store engine (cp.async.bulk shared -> global); the warp goes on to the next tile's FIR while the copy drains,
+// and waits for the copy to have READ shared memory just before the next STFT overwrites it.  Replaces the
+// LDS -> FFMA -> STG.CS loop whose warps sat on the store queue (24 % of the warp time for 7 % of the instructions).
+template <int ROWS, int NT, bool PK, bool TC = false, bool PS = false, int MINB = 0, bool BS = false>
 __global__ void __launch_bounds__(NT, MINB ? MINB : Cfg<ROWS, NT>::CTAS_PER_SM)
 dsp_tuned_kernel(const __grid_constant__ TunedArgs a) {
     static_assert(!PS || (!PK && !TC), "packed STFT: scalar FIR only");
@@ -479,6 +483,10 @@ dsp_tuned_kernel(const __grid_constant__ TunedArgs a) {
                 }
             }
         }
+        }
+        if constexpr (BS) {
+            // the previous tile's bulk stores must have read Ls before this tile's STFT writes it
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
         __syncthreads();
         // xs is free again: fetch the next tile while the STFT runs
@@ -722,6 +730,26 @@ dsp_tuned_kernel(const __grid_constant__ TunedArgs a) {
             const int tail = ROW_OUT - head - 4 * n4;
             const float4* s4 = reinterpret_cast<const float4*>(src + head);
             float4* d4 = reinterpret_cast<float4*>(dst + head);
+            if constexpr (BS) {
+                // warp w owns float4s [w * per, (w + 1) * per) of the 16-byte aligned body
+                constexpr int NW = NT / 32;
+                const int per = (n4 + NW - 1) / NW;
+                const int v0 = warp * per, v1 = (v0 + per < n4) ? v0 + per : n4;
+                float4* w4 = const_cast<float4*>(s4);
+                for (int v = v0 + lane; v < v1; v += 32) {
+                    const float4 l = w4[v];
+                    w4[v] = make_float4(fmaf(l.x, inv, c), fmaf(l.y, inv, c), fmaf(l.z, inv, c), fmaf(l.w, inv, c));
+                }
+                if (tid < head) __stcs(dst + tid, fmaf(src[tid], inv, c));
+                if (tid < tail) __stcs(dst + head + 4 * n4 + tid, fmaf(src[head + 4 * n4 + tid], inv, c));
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // normalised values -> bulk-copy engine
+                __syncwarp();
+                if (lane == 0 && v1 > v0) {
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 ::"l"(d4 + v0), "r"(smem_u32(w4 + v0)), "r"((unsigned)(16 * (v1 - v0))) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            } else {
             for (int v = tid; v < n4; v += NT) {
                 const float4 l = s4[v];
                 __stcs(d4 + v, make_float4(fmaf(l.x, inv, c), fmaf(l.y, inv, c), fmaf(l.z, inv, c),
@@ -729,9 +757,13 @@ dsp_tuned_kernel(const __grid_constant__ TunedArgs a) {
             }
             if (tid < head) __stcs(dst + tid, fmaf(src[tid], inv, c));
             if (tid < tail) __stcs(dst + head + 4 * n4 + tid, fmaf(src[head + 4 * n4 + tid], inv, c));
+            }
         }
         // The post-FIR barrier of the next iteration orders these reads of Ls / stat against the
         // next tile's STFT writes.
+    }
+    if constexpr (BS) {
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory stays valid until read
     }
 }
 
@@ -770,15 +802,15 @@ bool dsp_tuned_supported(const eegx_dsp_plan* p) {
 int dsp_tuned_table_floats() { return 8 * LANE_TABLE; }
 void dsp_tuned_fill_tables(float* host) { fill_lane_tables(host); }
 
-template <int ROWS, int NT, bool PK = false, bool TC = false, bool PS = false, int MINB = 0>
+template <int ROWS, int NT, bool PK = false, bool TC = false, bool PS = false, int MINB = 0, bool BS = false>
 int launch_variant(const TunedArgs& a, cudaStream_t st) {
     using C = Cfg<ROWS, NT>;
-    EEGX_CUDA_CHECK(cudaFuncSetAttribute(dsp_tuned_kernel<ROWS, NT, PK, TC, PS, MINB>,
+    EEGX_CUDA_CHECK(cudaFuncSetAttribute(dsp_tuned_kernel<ROWS, NT, PK, TC, PS, MINB, BS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
     const long long ntiles = (a.rows + ROWS - 1) / ROWS;
     const long long max_ctas = (long long)(MINB ? MINB : C::CTAS_PER_SM) * kNumSMsB200;
     const int grid = (int)(ntiles < max_ctas ? ntiles : max_ctas);
-    dsp_tuned_kernel<ROWS, NT, PK, TC, PS, MINB><<<grid, NT, C::SMEM_BYTES, st>>>(a);
+    dsp_tuned_kernel<ROWS, NT, PK, TC, PS, MINB, BS><<<grid, NT, C::SMEM_BYTES, st>>>(a);
     EEGX_CUDA_CHECK(cudaGetLastError());
     return EEGX_OK;
 }
@@ -799,6 +831,9 @@ int launch_dsp_tuned(const eegx_dsp_plan* plan, const DspArgs& d, cudaStream_t s
         case 4: return launch_variant<1, 96, true>(a, st);   // 1 row per tile, packed half-row FIR
         case 5: return launch_variant<1, 96, false, true>(a, st);    // 1 row per tile, FIR as 3xTF32 Toeplitz MMAs
         case 6: return launch_variant<1, 128, false, true>(a, st);   // same, 4 warps (16 FIR blocks divide evenly)
+        case 11: return launch_variant<1, 96, false, false, false, 0, true>(a, st);   // default kernel + bulk stores
+        case 12: return launch_variant<1, 128, false, false, false, 0, true>(a, st);  // same, 4 warps (3 CTAs/SM)
+        case 13: return launch_variant<2, 192, false, false, false, 0, true>(a, st);  // same, 2 rows per tile
         case 8: return launch_variant<1, 96, false, false, true>(a, st);   // scalar FIR + packed f32x2 STFT
         case 9: return launch_variant<1, 128, false, false, true, 4>(a, st);  // same, 4 warps x 4 CTAs/SM (128 registers)
         case 10: return launch_variant<1, 96, false, false, true, 5>(a, st);  // same, 3 warps x 5 CTAs/SM (136 registers)

@@ -82,3 +82,112 @@ class DenseHead:
         lab = label if label is not None else torch.zeros(x.shape[0], dtype=torch.int32, device=x.device)
         loss, probs, _ = self._run(x, lab, 0.0, False, False)
         return (probs, loss) if label is not None else probs
+
+
+# ------------------------------------------------------------------------------------------ convolution / max-pool front
+def _grid64(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not (torch.is_tensor(t) and t.is_cuda and t.dtype == torch.float64 and t.dim() == 2):
+        raise _lib.EegxError(f"{name} must be a 2-D CUDA float64 tensor (no CPU fallback)")
+    return t.contiguous()
+
+
+class Convolution:
+    """``Convolution(input_width, input_height, kernel_width, kernel_height, activation)`` of
+    ``wake_model/layers/convolution.h:11-13``: one ``(kernel_height, kernel_width)`` kernel and one bias, valid
+    cross-correlation; the activation string is stored and -- as in the reference -- never applied.  ``forward``
+    keeps the input for ``backward``, which returns the layer's input gradient and applies the SGD update in place
+    (``convolution.cpp:60-112``).  Initialisation: kernel uniform(-l, l) with l = sqrt(6 / (kw * kh)), bias
+    uniform(-0.05, 0.05) (``convolution.cpp:14-32``; the reference draws from ``std::random_device`` / ``rand()``)."""
+
+    def __init__(self, input_width: int, input_height: int, kernel_width: int, kernel_height: int, activation: str = "",
+                 device="cuda", generator: Optional[torch.Generator] = None):
+        if activation not in ACTIVATIONS:
+            raise ValueError(f"Unknown activation function: {activation}")
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise _lib.EegxError("Convolution runs on a CUDA device only (no CPU fallback)")
+        self.input_width, self.input_height = int(input_width), int(input_height)
+        self.kernel_width, self.kernel_height = int(kernel_width), int(kernel_height)
+        self.output_width, self.output_height = self.input_width - self.kernel_width + 1, self.input_height - self.kernel_height + 1
+        if self.output_width <= 0 or self.output_height <= 0:
+            raise ValueError("kernel larger than the input")
+        self.activation = activation
+        limit = math.sqrt(6.0 / (kernel_width * kernel_height))
+        u = lambda *shape: torch.rand(*shape, dtype=torch.float64, generator=generator)
+        self.kernel = ((2.0 * u(kernel_height, kernel_width) - 1.0) * limit).to(dev)
+        self.biases = ((u(1) - 0.5) * 0.1).to(dev)
+        self._input = None
+
+    def load(self, kernel, bias) -> "Convolution":
+        dev = self.kernel.device
+        k = torch.as_tensor(kernel, dtype=torch.float64).to(dev).contiguous().clone()
+        if k.shape != self.kernel.shape:
+            raise ValueError(f"kernel: expected shape {tuple(self.kernel.shape)}, got {tuple(k.shape)}")
+        self.kernel = k
+        self.biases = torch.as_tensor(bias, dtype=torch.float64).reshape(-1)[:1].to(dev).contiguous().clone()
+        return self
+
+    def forward(self, input_neurons: torch.Tensor) -> torch.Tensor:
+        x = _grid64(input_neurons, "input_neurons")
+        if tuple(x.shape) != (self.input_height, self.input_width):
+            raise ValueError(f"expected a ({self.input_height}, {self.input_width}) input, got {tuple(x.shape)}")
+        self._input = x
+        y = torch.empty(self.output_height, self.output_width, dtype=torch.float64, device=x.device)
+        _lib.check(_lib.lib().eegx_wake_conv2d_f64(
+            _lib.ptr(self.kernel), _lib.ptr(self.biases), _lib.ptr(x), self.input_height, self.input_width,
+            self.kernel_height, self.kernel_width, None, 0.0, _lib.ptr(y), None, _lib.stream_ptr()), "eegx_wake_conv2d_f64")
+        return y
+
+    def backward(self, output_gradient: torch.Tensor, learning_rate: float) -> torch.Tensor:
+        if self._input is None:
+            raise _lib.EegxError("Convolution.backward called before forward")
+        d = _grid64(output_gradient, "output_gradient")
+        if tuple(d.shape) != (self.output_height, self.output_width):
+            raise ValueError(f"expected a ({self.output_height}, {self.output_width}) gradient, got {tuple(d.shape)}")
+        dx = torch.empty_like(self._input)
+        _lib.check(_lib.lib().eegx_wake_conv2d_f64(
+            _lib.ptr(self.kernel), _lib.ptr(self.biases), _lib.ptr(self._input), self.input_height, self.input_width,
+            self.kernel_height, self.kernel_width, _lib.ptr(d), float(learning_rate), None, _lib.ptr(dx),
+            _lib.stream_ptr()), "eegx_wake_conv2d_f64")
+        return dx
+
+
+class MaxPool:
+    """``MaxPool(input_width, input_height, pool_width, pool_height, stride=1)`` of ``wake_model/layers/maxpool.h:11-20``:
+    first strict maximum of every window, its position kept for ``backward`` (``maxpool.cpp:6-69``)."""
+
+    def __init__(self, input_width: int, input_height: int, pool_width: int, pool_height: int, stride: int = 1):
+        self.input_width, self.input_height = int(input_width), int(input_height)
+        self.pool_width, self.pool_height, self.stride = int(pool_width), int(pool_height), int(stride)
+        if self.stride < 1:
+            raise ValueError("stride must be >= 1")
+        self.output_height = (self.input_height - self.pool_height) // self.stride + 1
+        self.output_width = (self.input_width - self.pool_width) // self.stride + 1
+        if self.output_width <= 0 or self.output_height <= 0:
+            raise ValueError("pooling window larger than the input")
+        self.max_indices = None
+        self._shape = None
+
+    def forward(self, input_neurons: torch.Tensor) -> torch.Tensor:
+        x = _grid64(input_neurons, "input_neurons")
+        if tuple(x.shape) != (self.input_height, self.input_width):
+            raise ValueError(f"expected a ({self.input_height}, {self.input_width}) input, got {tuple(x.shape)}")
+        y = torch.empty(self.output_height, self.output_width, dtype=torch.float64, device=x.device)
+        self.max_indices = torch.empty(self.output_height, self.output_width, 2, dtype=torch.int32, device=x.device)
+        self._x = x
+        _lib.check(_lib.lib().eegx_wake_maxpool_f64(
+            _lib.ptr(x), self.input_height, self.input_width, self.pool_width, self.pool_height, self.stride, None,
+            _lib.ptr(y), _lib.ptr(self.max_indices), None, _lib.stream_ptr()), "eegx_wake_maxpool_f64")
+        return y
+
+    def backward(self, output_gradient: torch.Tensor) -> torch.Tensor:
+        if self.max_indices is None:
+            raise _lib.EegxError("MaxPool.backward called before forward")
+        d = _grid64(output_gradient, "output_gradient")
+        if tuple(d.shape) != (self.output_height, self.output_width):
+            raise ValueError(f"expected a ({self.output_height}, {self.output_width}) gradient, got {tuple(d.shape)}")
+        dx = torch.empty_like(self._x)
+        _lib.check(_lib.lib().eegx_wake_maxpool_f64(
+            _lib.ptr(self._x), self.input_height, self.input_width, self.pool_width, self.pool_height, self.stride,
+            _lib.ptr(d), None, _lib.ptr(self.max_indices), _lib.ptr(dx), _lib.stream_ptr()), "eegx_wake_maxpool_f64")
+        return dx

@@ -386,6 +386,28 @@ int eegx_wake_dense_f64(double* w1, double* b1, double* w2, double* b2, const do
                         void* stream);
 
 /* ------------------------------------------------------------------------
+ * wake_model convolution / max-pool front (wake_model/train.cpp:26-33), fp64, one sample per call.
+ *
+ * eegx_wake_conv2d_f64 replaces Convolution::forward (wake_model/layers/convolution.cpp:36-57) and, when dout is
+ * given, Convolution::backward (:60-112) including its in-place SGD update of kernel and bias:
+ *   x (H, W), kernel (kh, kw), bias (1), y and dout (H-kh+1, W-kw+1), dx (H, W): row-major fp64 device buffers.
+ *   y = valid cross-correlation + bias (the constructor's activation is never applied by the reference).
+ *   dout != NULL: dx = the layer's "input gradient" as written (flipped kernel at input position (y+ky, x+kx)),
+ *   computed with the kernel BEFORE the update; then kernel -= lr * kernel_gradient, bias -= lr * sum(dout).
+ *   y may be NULL (backward only).
+ * eegx_wake_maxpool_f64 replaces MaxPool::forward (wake_model/layers/maxpool.cpp:6-43) and ::backward (:46-69):
+ *   y (OH, OW) with OH = (H-pool_h)/stride+1, OW = (W-pool_w)/stride+1; argmax (OH, OW, 2) int32 = the recorded
+ *   (row, col) of the first strict maximum, (-1, -1) if the window saw no element (the reference bounds rows by a
+ *   member that maxpool.h:15 sets to the input WIDTH); dx (H, W) = scatter-add of dout to the maxima.
+ * Every result is bit-exact against the reference's compiled classes (tests/test_wake.py): one thread owns one
+ * output element and adds its terms in the reference's loop order without FMA contraction.
+ * ------------------------------------------------------------------------ */
+int eegx_wake_conv2d_f64(double* kernel, double* bias, const double* x, int64_t H, int64_t W, int64_t kh, int64_t kw,
+                         const double* dout, double lr, double* y, double* dx, void* stream);
+int eegx_wake_maxpool_f64(const double* x, int64_t H, int64_t W, int64_t pool_w, int64_t pool_h, int64_t stride,
+                          const double* dout, double* y, int32_t* argmax, double* dx, void* stream);
+
+/* ------------------------------------------------------------------------
  * Beam-search step: log-softmax + top-k of every logits row in one read (generation.py).
  * Replaces the per-step log_softmax / add / torch.topk over (batch*beams, V) fp32 logits of transformers'
  * GenerationMixin._beam_search (third-party; called from main_model/src/models/bart_decoder.py:59-79).

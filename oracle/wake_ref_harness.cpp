@@ -1,15 +1,18 @@
 // TEST INFRASTRUCTURE -- drives the REFERENCE's own wake_model code (compiled from /root/reference where it lies,
 // never copied) through the same C signature as oracle/wake_dense_oracle.c so the restatement can be pinned bit-exactly.
 //
-// Links wake_model/layers/linear.cpp and includes layers/linear.h, layers/activations.h, layers/losses.h; the loop
+// Links wake_model/layers/linear.cpp, convolution.cpp and maxpool.cpp and includes their headers, layers/activations.h
+// and layers/losses.h; the loop
 // below is the Linear-only part of wake_model/train.cpp:68-117 (forward through both layers, loss, delta, backward).
 // The full program cannot serve as an oracle: it needs a dataset that is not shipped and reads out of bounds
 // (SURVEY.md section 2), so only these leaf classes are exercised.
 #include <string>
 #include <vector>
 
+#include "layers/convolution.h"
 #include "layers/linear.h"
 #include "layers/losses.h"
+#include "layers/maxpool.h"
 
 static const char* act_name(int act) {
     switch (act) {
@@ -57,5 +60,55 @@ extern "C" int wake_dense_ref(double* w1, double* b1, double* w2, double* b2, co
         for (int j = 0; j < hidden; ++j) w2[(long)k * hidden + j] = l2.weights[k][j];
         b2[k] = l2.biases[k];
     }
+    return 0;
+}
+
+
+// ---- the convolution / max-pool front (wake_model/train.cpp:26-33): the reference's own classes, same C signatures as
+// oracle/wake_conv_oracle.c ----
+static std::vector<std::vector<Neuron>> to_grid(const double* x, int H, int W) {
+    std::vector<std::vector<Neuron>> g(H, std::vector<Neuron>(W));
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) g[i][j].output = x[(long)i * W + j];
+    return g;
+}
+
+extern "C" int wake_conv2d_ref(double* kernel, double* bias, const double* x, int H, int W, int kh, int kw,
+                               const double* dout, double lr, double* y, double* dx) {
+    Convolution conv(W, H, kw, kh, "relu");
+    for (int a = 0; a < kh; ++a)
+        for (int b = 0; b < kw; ++b) conv.kernel[a][b] = kernel[a * kw + b];
+    conv.biases[0] = bias[0];
+    const int OH = conv.output_height, OW = conv.output_width;
+    std::vector<std::vector<Neuron>> out = conv.forward(to_grid(x, H, W));
+    if (y)
+        for (int i = 0; i < OH; ++i)
+            for (int j = 0; j < OW; ++j) y[(long)i * OW + j] = out[i][j].output;
+    if (!dout) return 0;
+    std::vector<std::vector<Neuron>> gin = conv.backward(to_grid(dout, OH, OW), lr);
+    if (dx)
+        for (int i = 0; i < H; ++i)
+            for (int j = 0; j < W; ++j) dx[(long)i * W + j] = gin[i][j].output;
+    for (int a = 0; a < kh; ++a)
+        for (int b = 0; b < kw; ++b) kernel[a * kw + b] = conv.kernel[a][b];
+    bias[0] = conv.biases[0];
+    return 0;
+}
+
+extern "C" int wake_maxpool_ref(const double* x, int H, int W, int pw, int ph, int stride, const double* dout, double* y,
+                                int* argmax, double* dx) {
+    MaxPool pool(W, H, pw, ph, stride);
+    const int OH = pool.output_height, OW = pool.output_width;
+    std::vector<std::vector<Neuron>> out = pool.forward(to_grid(x, H, W));
+    for (int i = 0; i < OH; ++i)
+        for (int j = 0; j < OW; ++j) {
+            if (y) y[(long)i * OW + j] = out[i][j].output;
+            argmax[2 * ((long)i * OW + j)] = pool.max_indices[i][j].first;
+            argmax[2 * ((long)i * OW + j) + 1] = pool.max_indices[i][j].second;
+        }
+    if (!dout || !dx) return 0;
+    std::vector<std::vector<Neuron>> gin = pool.backward(to_grid(dout, OH, OW));
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) dx[(long)i * W + j] = gin[i][j].output;
     return 0;
 }

@@ -174,3 +174,142 @@ def test_cuda_training_reduces_loss_at_config_shape():
             first = float(loss.mean())
         assert torch.allclose(probs.sum(1), torch.ones(16, dtype=torch.float64, device="cuda"), atol=1e-12)
     assert float(loss.mean()) < 0.2 * first
+
+
+# ------------------------------------------------------------------------------------------ convolution / max-pool front
+CONV_GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "wake_conv_ref.npz")
+
+
+def _conv_cases():
+    z = np.load(CONV_GOLDEN)
+    for ci in range(int(z["n_conv"])):
+        pre = f"conv{ci}_"
+        yield ({k: z[pre + "in_" + k] for k in ("x", "kernel", "bias", "dout")},
+               {k: z[pre + "out_" + k] for k in ("y", "dx", "kernel", "bias")})
+
+
+def _pool_cases():
+    z = np.load(CONV_GOLDEN)
+    for ci in range(int(z["n_pool"])):
+        pre = f"pool{ci}_"
+        yield (tuple(int(v) for v in z[pre + "cfg"]), z[pre + "in_x"], z[pre + "in_dout"],
+               {k: z[pre + "out_" + k] for k in ("y", "argmax", "dx")})
+
+
+def test_conv_oracle_matches_reference_golden_bit_exact():
+    """oracle/wake_conv_oracle.c against vectors the reference's own Convolution / MaxPool classes produced
+    (tests/golden/make_wake_conv_golden.py): every double and every argmax identical."""
+    conv, pool = wake_oracle.conv_oracle()
+    for inp, want in _conv_cases():
+        got = wake_oracle.run_conv(conv, inp["kernel"], inp["bias"], inp["x"], inp["dout"], lr=0.1)
+        for k in want:
+            assert np.array_equal(got[k], want[k]), k
+    for (pw, ph, s), x, d, want in _pool_cases():
+        got = wake_oracle.run_maxpool(pool, x, pw, ph, s, d)
+        for k in want:
+            assert np.array_equal(got[k], want[k]), k
+
+
+def test_conv_oracle_matches_compiled_reference_on_random_problems():
+    rconv, rpool = wake_oracle.conv_reference()
+    if rconv is None or rpool is None:
+        pytest.skip("oracle/_ref/libwake_ref.so not built here (needs /root/reference); golden vectors cover it")
+    conv, pool = wake_oracle.conv_oracle()
+    rng = np.random.default_rng(5)
+    for _ in range(12):
+        H, kh = int(rng.integers(1, 6)), 1
+        kh = int(rng.integers(1, H + 1))
+        W = int(rng.integers(8, 90))
+        kw = int(rng.integers(1, W + 1))
+        x, k = rng.normal(0, 1, (H, W)), rng.normal(0, 0.3, (kh, kw))
+        d = rng.normal(0, 1, (H - kh + 1, W - kw + 1))
+        a, b = wake_oracle.run_conv(conv, k, 0.01, x, d, 0.05), wake_oracle.run_conv(rconv, k, 0.01, x, d, 0.05)
+        assert all(np.array_equal(a[n], b[n]) for n in ("y", "dx", "kernel", "bias"))
+        ph, pw, s = int(rng.integers(1, H + 1)), int(rng.integers(1, 5)), int(rng.integers(1, 4))
+        xq = np.round(x, 1)
+        dd = rng.normal(0, 1, ((H - ph) // s + 1, (W - pw) // s + 1))
+        a, b = wake_oracle.run_maxpool(pool, xq, pw, ph, s, dd), wake_oracle.run_maxpool(rpool, xq, pw, ph, s, dd)
+        assert all(np.array_equal(a[n], b[n]) for n in ("y", "argmax", "dx"))
+
+
+@pytest.mark.gpu
+def test_cuda_conv_front_is_bit_exact_against_the_reference_golden():
+    from imagined_speech_translation_b200.wake import Convolution, MaxPool
+    for inp, want in _conv_cases():
+        H, W = inp["x"].shape
+        kh, kw = inp["kernel"].shape
+        conv = Convolution(W, H, kw, kh, "relu").load(inp["kernel"], inp["bias"])
+        y = conv.forward(torch.from_numpy(inp["x"]).cuda())
+        dx = conv.backward(torch.from_numpy(inp["dout"]).cuda(), 0.1)
+        assert np.array_equal(y.cpu().numpy(), want["y"])
+        assert np.array_equal(dx.cpu().numpy(), want["dx"])
+        assert np.array_equal(conv.kernel.cpu().numpy(), want["kernel"])
+        assert np.array_equal(conv.biases.cpu().numpy(), want["bias"])
+    for (pw, ph, s), x, d, want in _pool_cases():
+        H, W = x.shape
+        pool = MaxPool(W, H, pw, ph, s)
+        y = pool.forward(torch.from_numpy(x).cuda())
+        dx = pool.backward(torch.from_numpy(d).cuda())
+        assert np.array_equal(y.cpu().numpy(), want["y"])
+        assert np.array_equal(pool.max_indices.cpu().numpy(), want["argmax"])
+        assert np.array_equal(dx.cpu().numpy(), want["dx"])
+
+
+@pytest.mark.gpu
+def test_cuda_conv_front_at_the_train_cpp_shapes_matches_the_oracle():
+    """wake_model/train.cpp:26-33 on a 2 x 4096 input: conv 32x1 -> pool 2x1 -> conv 64x1 -> pool -> conv 128x1 -> pool,
+    forward and backward through the chain, every tensor bit-identical to the C oracle run on the same data."""
+    from imagined_speech_translation_b200.wake import Convolution, MaxPool
+    oconv, opool = wake_oracle.conv_oracle()
+    rng = np.random.default_rng(11)
+    H, W = 2, 4096
+    x = rng.normal(0, 1, (H, W))
+    layers, cur_w = [], W
+    for kw in (32, 64, 128):
+        c = Convolution(cur_w, H, kw, 1, "relu", generator=torch.Generator().manual_seed(kw))
+        p = MaxPool(c.output_width, c.output_height, 2, 1)
+        layers += [c, p]
+        cur_w = p.output_width
+    acts, h = [], torch.from_numpy(x).cuda()
+    ref_acts, hr = [], x
+    params = [(l.kernel.cpu().numpy().copy(), l.biases.cpu().numpy().copy()) if isinstance(l, Convolution) else None
+              for l in layers]
+    for l, prm in zip(layers, params):
+        h = l.forward(h)
+        acts.append(h)
+        if prm is not None:
+            hr_out = wake_oracle.run_conv(oconv, prm[0], prm[1], hr)["y"]
+        else:
+            hr_out = wake_oracle.run_maxpool(opool, hr, 2, 1, 1)["y"]
+        ref_acts.append((hr, hr_out))
+        hr = hr_out
+        assert np.array_equal(h.cpu().numpy(), hr)
+    g = rng.normal(0, 0.1, hr.shape)
+    gd = torch.from_numpy(g).cuda()
+    for l, prm, (xin, _) in zip(reversed(layers), reversed(params), reversed(ref_acts)):
+        if prm is not None:
+            gd = l.backward(gd, 0.1)
+            r = wake_oracle.run_conv(oconv, prm[0], prm[1], xin, g, 0.1)
+            assert np.array_equal(l.kernel.cpu().numpy(), r["kernel"]) and np.array_equal(l.biases.cpu().numpy(), r["bias"])
+        else:
+            gd = l.backward(gd)
+            r = wake_oracle.run_maxpool(opool, xin, 2, 1, 1, g)
+        g = r["dx"]
+        assert np.array_equal(gd.cpu().numpy(), g)
+
+
+@pytest.mark.gpu
+def test_cuda_conv_front_rejects_bad_arguments():
+    from imagined_speech_translation_b200 import _lib
+    from imagined_speech_translation_b200.wake import Convolution, MaxPool
+    with pytest.raises(ValueError):
+        Convolution(8, 2, 9, 1)
+    with pytest.raises(ValueError):
+        MaxPool(8, 2, 2, 3)
+    c = Convolution(16, 2, 4, 1)
+    with pytest.raises(_lib.EegxError):
+        c.forward(torch.zeros(2, 16, dtype=torch.float64))               # CPU tensor: no fallback
+    with pytest.raises(_lib.EegxError):
+        c.backward(torch.zeros(2, 13, dtype=torch.float64, device="cuda"), 0.1)   # before forward
+    with pytest.raises(ValueError):
+        c.forward(torch.zeros(2, 15, dtype=torch.float64, device="cuda"))
