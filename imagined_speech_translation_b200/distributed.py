@@ -86,6 +86,45 @@ def allreduce_gradients(params: Sequence[torch.nn.Parameter], group=None, averag
     return calls
 
 
+_registered_pools: list = []      # (backend, pool): NCCL-registered allocations that must be deregistered before teardown
+
+
+def nccl_registered_zeros(n: int, device) -> Optional[torch.Tensor]:
+    """A zero-filled fp32 buffer of n elements allocated through NCCL's own allocator (``ncclMemAlloc``) and
+    registered with the communicator, so that all-reduces on it (and on slices of it) run zero-copy: with NVLink
+    SHARP (NVLS) the reduction happens in the switch on the user buffer itself, with fewer NCCL CTAs taking SMs from
+    the backward kernels they overlap.  Returns None -- the caller allocates normally -- outside a multi-rank NCCL
+    job, when ``EEGX_NCCL_REGISTER=0``, or when this torch / NCCL build lacks the hooks."""
+    if os.environ.get("EEGX_NCCL_REGISTER", "1") == "0":
+        return None
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return None
+    if dist.get_backend() != "nccl" or not hasattr(torch.cuda, "MemPool"):
+        return None
+    try:
+        backend = dist.distributed_c10d._get_default_group()._get_backend(torch.device(device))
+        pool = torch.cuda.MemPool(backend.mem_allocator)
+        with torch.cuda.use_mem_pool(pool):
+            t = torch.zeros(n, device=device, dtype=torch.float32)
+        backend.register_mem_pool(pool)
+    except Exception as exc:       # older NCCL / no allocator support: plain memory works, only slower
+        import warnings
+        warnings.warn(f"NCCL buffer registration unavailable ({exc!r}); using an unregistered gradient buffer")
+        return None
+    _registered_pools.append((backend, pool))
+    return t
+
+
+def release_registered_buffers() -> None:
+    """Deregister the NCCL-allocated pools (before the process group is destroyed)."""
+    while _registered_pools:
+        backend, pool = _registered_pools.pop()
+        try:
+            backend.deregister_mem_pool(pool)
+        except Exception:
+            pass
+
+
 SHUTDOWN_STALLED_EXIT = 75      # EX_TEMPFAIL: teardown (graph release / barrier / destroy) did not finish in time
 
 
@@ -116,7 +155,9 @@ def shutdown(trainer=None, grace_s: float = 30.0) -> None:
         trainer.release_graph()
     if dist.is_available() and dist.is_initialized():
         try:
+            torch.cuda.synchronize() if torch.cuda.is_available() else None
             dist.barrier()
+            release_registered_buffers()
         finally:
             dist.destroy_process_group()
     timer.cancel()

@@ -94,7 +94,13 @@ class FlatAdamW(torch.optim.Optimizer):
         if not any(ps for ps, _ in plan):
             raise _lib.EegxError("FlatAdamW.step() called before any backward pass")
         dev = next(ps[0].device for ps, _ in plan if ps)
-        self._all_grads = torch.zeros(sum(sum(sz) for _, sz in plan), device=dev)
+        n_grads = sum(sum(sz) for _, sz in plan)
+        from . import distributed as _dp
+        # in a multi-rank NCCL job the gradient buffer comes from NCCL's allocator and is registered with the
+        # communicator (zero-copy / NVLS all-reduce on the buffer itself); otherwise plain device memory
+        self._all_grads = _dp.nccl_registered_zeros(n_grads, dev)
+        if self._all_grads is None:
+            self._all_grads = torch.zeros(n_grads, device=dev)
         flats, base = [], 0
         self._offsets = {}         # id(param) -> (offset, padded length) inside _all_grads
         for ps, sizes in plan:

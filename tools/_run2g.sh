@@ -1,4 +1,4 @@
-run() { tag=$1; shift; env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 15 --warmup 4 > gpurun_out/r2_n2_$tag.json 2> gpurun_out/r2_n2_$tag.err; python - <<PY
+run() { tag=$1; shift; env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 15 --warmup 4 > gpurun_out/r2_n2_$tag.json 2> gpurun_out/r2_n2_$tag.err; echo "rc=$?"; python - <<PY
 import json
 ok=False
 for l in open('gpurun_out/r2_n2_$tag.json'):
@@ -6,9 +6,7 @@ for l in open('gpurun_out/r2_n2_$tag.json'):
         d=json.loads(l); print('$tag', round(d['value']), round(d['ms_per_step'],2), round(d['e2e']['value'])); ok=True
 if not ok: print('$tag FAILED')
 PY
+grep -h -i "warn\|error\|NVLS\|registr" gpurun_out/r2_n2_$tag.err | head -5
 }
-run default X=1
-run hiprio TORCH_NCCL_HIGH_PRIORITY=1
-run ctas16 NCCL_MAX_CTAS=16
-run ctas32 NCCL_MAX_CTAS=32
-run nooverlap EEGX_OVERLAP_ALLREDUCE=0
+run reg EEGX_NCCL_REGISTER=1 NCCL_DEBUG=WARN
+run noreg EEGX_NCCL_REGISTER=0
