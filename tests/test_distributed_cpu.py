@@ -147,3 +147,11 @@ def test_grad_runs_merge_adjacent_slices():
     assert opt.grad_runs([ps[0], ps[2], ps[3]]) == [(0, 8), (24, 56)]
     assert opt.grad_runs([ps[3], ps[1]]) == [(8, 24), (32, 56)]
     assert opt.grad_runs([torch.nn.Parameter(torch.zeros(3))]) == []      # no gradient slot: skipped
+
+
+def test_registered_gradient_buffer_is_optional():
+    """Outside a multi-rank NCCL job (single process, gloo, or EEGX_NCCL_REGISTER=0) the NCCL-registered allocation
+    is simply not used: the helper returns None and the optimizer falls back to plain device memory."""
+    from imagined_speech_translation_b200 import distributed as dp
+    assert dp.nccl_registered_zeros(16, "cpu") is None
+    dp.release_registered_buffers()          # nothing registered: a no-op
