@@ -1,12 +1,13 @@
-run() { tag=$1; shift; env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 15 --warmup 4 > gpurun_out/r2_n2_$tag.json 2> gpurun_out/r2_n2_$tag.err; echo "rc=$?"; python - <<PY
+timeout 300 python -m pytest tests/test_train_gpu.py -x -q -m gpu -k "two_gpus" 2>&1 | tail -1
+run() { tag=$1; shift; env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 15 --warmup 4 > gpurun_out/r2_n2_$tag.json 2> gpurun_out/r2_n2_$tag.err; python - <<PY
 import json
-ok=False
-for l in open('gpurun_out/r2_n2_$tag.json'):
-    if l.startswith('{'):
-        d=json.loads(l); print('$tag', round(d['value']), round(d['ms_per_step'],2), round(d['e2e']['value'])); ok=True
-if not ok: print('$tag FAILED')
+s=open('gpurun_out/r2_n2_$tag.json').read()
+try:
+    i=s.index('{"torch_b200"'); d,_=json.JSONDecoder().raw_decode(s[i:])
+    print('$tag', round(d['value']), round(d['ms_per_step'],2), round(d['e2e']['value']))
+except Exception as e: print('$tag FAILED', e)
 PY
-grep -h -i "warn\|error\|NVLS\|registr" gpurun_out/r2_n2_$tag.err | head -5
 }
-run reg EEGX_NCCL_REGISTER=1 NCCL_DEBUG=WARN
-run noreg EEGX_NCCL_REGISTER=0
+run sidejoin X=1
+run mainjoin EEGX_BOUNDARY_JOIN=1
+run sidejoin2 X=1
