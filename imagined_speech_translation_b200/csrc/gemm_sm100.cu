@@ -803,7 +803,7 @@ extern "C" int eegx_gemm_bf16(const eegx_gemm_desc* d, const void* A, const void
     // Tile width by a wave-quantisation cost model: a launch takes `rounds` passes of the 148 SMs (74 CTA
     // pairs) over the tiles and a pass costs ~ BLOCK_N x a per-width efficiency factor (narrow tiles
     // move more operand bytes per MAC; measured with tools/bench_gemm.py).
-    static const int env_2cta = [] { const char* v = getenv("EEGX_GEMM_2CTA"); return v ? atoi(v) : 1; }();
+    static const int env_2cta = [] { const char* v = getenv("EEGX_GEMM_2CTA"); return v ? atoi(v) : 3; }();
     const bool bm_ = d->b_mn_major != 0;
     auto rounds_for = [&](int bn, bool pr) {
         const long long mb_ = pr ? (d->M + 2 * BLOCK_M - 1) / (2 * BLOCK_M) : (d->M + BLOCK_M - 1) / BLOCK_M;
@@ -811,10 +811,13 @@ extern "C" int eegx_gemm_bf16(const eegx_gemm_desc* d, const void* A, const void
         const long long slots = pr ? eegx::kNumSMsB200 / 2 : eegx::kNumSMsB200;
         return (double)((t + slots - 1) / slots);
     };
-    // CTA pairs (cta_group::2, 256-row tiles) pay off on the large problems only (tools/bench_gemm.py:
-    // +16 % on the 4096 x 51264 x 768 LM head, +5 % at 8192^3, -3..6 % on the 768-wide encoder GEMMs, and
-    // the pairs co-schedule worse when four region streams share the GPU): EEGX_GEMM_2CTA=2 forces them.
-    const bool want_pair = env_2cta != 0 && d->M > BLOCK_M && (env_2cta >= 2 || d->N >= 8192 || d->K >= 4096);
+    // CTA pairs (cta_group::2, 256-row tiles).  Stand-alone (tools/bench_gemm.py) they gain +16 % on the
+    // 4096 x 51264 x 768 LM head and +5 % at 8192^3 but lose 3..6 % on a single 768-wide encoder GEMM.  Inside the
+    // step the lock-step region encoders launch those GEMMs with four times the rows, and there the pairs win:
+    // EEGX_GEMM_2CTA = 1 (large N / K only) 26.76 ms/step, 2 (always) 26.35, 3 (default: large N / K, or >= 16384 rows
+    // over all problems of the launch) 26.16 ms/step at B = 256 (profiles/r2_gemm_pair_policy.txt).  0 = never.
+    const bool want_pair = env_2cta != 0 && d->M > BLOCK_M &&
+                           (env_2cta == 2 || d->N >= 8192 || d->K >= 4096 || (env_2cta == 3 && d->M * problems >= 16384));
     int block_n = 128;
     {
         const int cand[4] = {64, 128, 192, 256};
