@@ -116,6 +116,7 @@ class EEGTrainer:
         self._plan = None
         self._plan_lock_step = None
         self._works = []
+        self._fired = set()
         self._grads_reduced = False
         self._graph_reduces = False
         self.best_bleu4 = 0.0
@@ -213,7 +214,8 @@ class EEGTrainer:
 
     def _on_boundary(self, key):
         runs = self._overlap_plan().get(key)
-        if runs:
+        if runs and key not in self._fired:
+            self._fired.add(key)
             fused.join_side()          # weight gradients deferred to the side stream belong to the slice as well
             self._reduce_runs(runs)
 
@@ -285,12 +287,19 @@ class EEGTrainer:
             (out.loss / self.config['accumulation_steps']).backward()
             return out.loss.detach()
         self._works = []
+        self._fired = set()
         fused.set_grad_boundary_callback(self._on_boundary)          # before forward: the boundaries are tape nodes
         try:
             out = self._forward_loss(batch)
             (out.loss / self.config['accumulation_steps']).backward()
         finally:
             fused.set_grad_boundary_callback(None)
+        # slices whose boundary did not fire in this backward pass (the plan assumed the lock-step region path but the
+        # batch took the per-region one, or the other way round; a sequence length the fused attention does not
+        # serve; ...) are reduced now, with the rest: every gradient is reduced exactly once whatever path ran
+        for key, runs in self._overlap_plan().items():
+            if key != 'rest' and key not in self._fired:
+                self._reduce_runs(runs)
         self._reduce_runs(self._overlap_plan()['rest'])
         for w in self._works:
             w.wait()                             # the compute stream waits for the NCCL stream (no host sync)

@@ -90,6 +90,20 @@ def main():
         else:
             ok = bool(((got - base).abs().max() / base.abs().max()) <= 1e-6)
         results[name] = ok
+    # plan / path mismatch: the plan was laid out for the lock-step region path, the batch takes the per-region one (as
+    # happens for channel counts the stacked kernels do not serve).  The slices whose boundaries never fire must still
+    # be reduced exactly once.
+    enc = model.brain_encoder
+    if any(isinstance(k, tuple) and k[1] == 'group' for k in plan):
+        saved = enc._lock_step
+        enc._lock_step = lambda eeg_data: None
+        try:
+            base_pr = reduced_grads(False, False)
+            got_pr = reduced_grads(True, False)
+        finally:
+            enc._lock_step = saved
+        results["per_region_path_under_lock_step_plan"] = (torch.equal(got_pr, base_pr) if world == 2 else
+                                                           bool(((got_pr - base_pr).abs().max() / base_pr.abs().max()) <= 1e-6))
     flags = torch.tensor([int(v) for v in results.values()], device=dev)
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     timing = {}
