@@ -418,7 +418,7 @@ def run_ours(args, rank, world, local_rank):
 
     def step(batch):
         loss = trainer.train_step(batch)
-        trainer._optimizer_step(step_scheduler=True)
+        trainer.optimizer_step(step_scheduler=True)
         return loss
 
     for i in range(2):

@@ -219,6 +219,11 @@ class EEGTrainer:
             fused.join_side()          # weight gradients deferred to the side stream belong to the slice as well
             self._reduce_runs(runs)
 
+    def optimizer_step(self, step_scheduler: bool = True):
+        """Public form of the step `train_epoch` takes every `accumulation_steps` micro-batches (reference
+        trainer.py:101-113): gradient all-reduce if still pending, clip, AdamW, zero_grad, scheduler."""
+        return self._optimizer_step(step_scheduler)
+
     def _optimizer_step(self, step_scheduler: bool):
         clip = self.config.get('grad_clip_norm', 1.0)
         if isinstance(self.optimizer, FlatAdamW):

@@ -76,7 +76,7 @@ def main():
 
     trainer.overlap_allreduce = False
     trainer.train_step(batch)                     # first step: builds the flat buffers (lr = 0 at step 0: weights unchanged)
-    trainer._optimizer_step(step_scheduler=False)
+    trainer.optimizer_step(step_scheduler=False)
     base = reduced_grads(False, False)
     plan = trainer._overlap_plan()
     n_total = opt._all_grads.numel()
@@ -114,12 +114,12 @@ def main():
             opt.zero_grad()
             trainer.capture(batch, warmup=0)
             for _ in range(5):
-                trainer.train_step(batch); trainer._optimizer_step(step_scheduler=True)
+                trainer.train_step(batch); trainer.optimizer_step(step_scheduler=True)
             dist.barrier(); torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(20):
-                trainer.train_step(batch); trainer._optimizer_step(step_scheduler=True)
+                trainer.train_step(batch); trainer.optimizer_step(step_scheduler=True)
             e1.record()
             dist.barrier(); torch.cuda.synchronize()
             t = torch.tensor([e0.elapsed_time(e1) / 20], device=dev)

@@ -23,11 +23,11 @@ labels = torch.randint(1, 51271, (B, 16), device="cuda", generator=g); labels[:,
 ids = torch.cat([torch.full((B, 1), 101, device="cuda"), labels[:, :-1].clamp_min(0)], 1)
 batch = {'raw': 20 * torch.randn(B, C, T, device="cuda", generator=g), 'decoder_input_ids': ids, 'labels': labels}
 for _ in range(3):
-    t.train_step(batch); t._optimizer_step(True)
+    t.train_step(batch); t.optimizer_step(True)
 torch.cuda.synchronize()
 torch.cuda._sleep(int(0.2 * 1.9e9))
 ops.GEMM_TIMING = []
-t.train_step(batch); t._optimizer_step(True)
+t.train_step(batch); t.optimizer_step(True)
 torch.cuda.synchronize()
 rec, ops.GEMM_TIMING = ops.GEMM_TIMING, None
 agg = collections.defaultdict(lambda: [0, 0.0, 0.0])

@@ -30,7 +30,7 @@ batch = {'raw': raw, 'decoder_input_ids': ids, 'labels': labels}
 
 def step():
     loss = t.train_step(batch)
-    t._optimizer_step(True)
+    t.optimizer_step(True)
     return loss
 
 for _ in range(3): step()
