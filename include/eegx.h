@@ -20,6 +20,9 @@
  *     void*; NULL = legacy default stream); no host sync, no allocation inside
  *     compute calls, so they are CUDA-graph capturable.
  *   - plans own only O(KB) constant tables (FIR taps, window, twiddles).
+ *   - grids are sized for B200: the SM count (148) is a compile-time constant of the library
+ *     (csrc/eegx_common.h, kNumSMsB200) -- persistent kernels launch one CTA (or CTA pair, or a fixed
+ *     number of CTAs) per SM of that part, and the sm_100 check above is what keeps other devices out.
  */
 #ifndef EEGX_H
 #define EEGX_H
